@@ -1,0 +1,13 @@
+"""f16_mpc_oop_py_b200 -- B200-native batched F-16 plant behind the reference's ctypes C ABI.
+
+Only the hot path of johnviljoen/f16_mpc_oop_py lives here: Nlplant / atmos, the aero-table interpolation, the
+env.py Euler step and the finite-difference linearise, as hand-written sm_100a CUDA in libf16_b200.so.  Importing
+this package loads that library and fails if it has not been built; there is no CPU fallback.
+"""
+from . import parameters
+from ._lib import (CLR_AS_BUILT, CLR_FROM_FILE, FD_CENTRAL, FD_FORWARD, MATH_FAST, MATH_STRICT, F16Error, LqrLaw, init,
+                   lib)
+from .plant import F16Batch, atmos, make_lqr, nlplant
+
+__all__ = ["F16Batch", "F16Error", "LqrLaw", "atmos", "init", "lib", "make_lqr", "nlplant", "parameters",
+           "MATH_STRICT", "MATH_FAST", "CLR_AS_BUILT", "CLR_FROM_FILE", "FD_FORWARD", "FD_CENTRAL"]

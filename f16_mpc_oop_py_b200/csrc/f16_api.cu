@@ -1,0 +1,664 @@
+// f16_api.cu -- the C ABI of libf16_b200.so (include/f16_b200.h): library state, table upload, host<->device
+// plumbing and dispatch into the strict / fast kernel builds.  No arithmetic of the plant happens on the host.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/f16_b200.h"
+#include "f16_kernels.cuh"
+#include "f16_tables_host.h"
+
+static_assert(sizeof(f16_lqr_t) == sizeof(f16::LqrLaw), "f16_lqr_t and the device-side law must have one layout");
+
+namespace {
+
+struct DevBuf {  // grow-only device scratch for the host-pointer entry points
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct State {
+  bool ready = false;
+  int init_rc = F16_ERR_NOINIT;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<double> payload;
+  std::string table_source;
+  double* d_hifi = nullptr;
+  double* d_lofi = nullptr;
+  int math_mode = F16_MATH_STRICT;
+  int clr_mode = F16_CLR_AS_BUILT;
+  bool smem_tables = true;
+  int step_threads = 256;
+  double default_xcg = 0.25;
+  int last_status = 0;
+  unsigned long long launches = 0;
+  // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
+  double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
+  double* pin_dev = nullptr;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush;
+};
+
+State G;
+std::mutex G_mu;
+thread_local std::string t_err;
+
+void set_err(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_err("%s: %s", what, cudaGetErrorString(e));
+  return F16_ERR_CUDA;
+}
+#define CK(call)                                          \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+std::string lib_dir() {
+  Dl_info info;
+  if (dladdr((void*)&f16_init, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t s = p.rfind('/');
+    return s == std::string::npos ? std::string(".") : p.substr(0, s);
+  }
+  return std::string();
+}
+
+int upload_tables() {
+  std::vector<double> img;
+  f16::build_hifi_image(G.payload, G.clr_mode == F16_CLR_FROM_FILE, img);
+  if (!G.d_hifi) CK(cudaMalloc(&G.d_hifi, F16_IMG_HIFI_BYTES));
+  CK(cudaMemcpy(G.d_hifi, img.data(), F16_IMG_HIFI_BYTES, cudaMemcpyHostToDevice));
+  f16::build_lofi_image(img);
+  if (!G.d_lofi) CK(cudaMalloc(&G.d_lofi, F16_IMG_LOFI_BYTES));
+  CK(cudaMemcpy(G.d_lofi, img.data(), F16_IMG_LOFI_BYTES, cudaMemcpyHostToDevice));
+  return F16_OK;
+}
+
+int init_locked(const char* table_path, int device) {
+  if (G.ready) return F16_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device: %s (libf16_b200 has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    return G.init_rc = F16_ERR_CUDA;
+  }
+  if (device < 0) {
+    const char* v = getenv("F16_DEVICE");
+    if (!v || !*v) v = getenv("LOCAL_RANK");
+    device = (v && *v) ? atoi(v) % ndev : 0;
+  }
+  if (device >= ndev) { set_err("device %d out of range (%d present)", device, ndev); return G.init_rc = F16_ERR_ARG; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_err("device %d is sm_%d%d; libf16_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return G.init_rc = F16_ERR_CUDA;
+  }
+  G.device = device;
+  G.sm_count = prop.multiProcessorCount;
+
+  std::string err;
+  if (!f16::load_canonical(table_path, lib_dir(), G.payload, G.table_source, err)) {
+    set_err("%s", err.c_str());
+    return G.init_rc = F16_ERR_TABLES;
+  }
+  if (!f16::check_grids(G.payload, err)) { set_err("%s", err.c_str()); return G.init_rc = F16_ERR_TABLES; }
+
+  CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&G.ev0));
+  CK(cudaEventCreate(&G.ev1));
+  CK(cudaHostAlloc((void**)&G.pin, 64 * sizeof(double), cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void**)&G.pin_dev, G.pin, 0));
+
+  if (const char* v = getenv("F16_XCG")) G.default_xcg = atof(v);
+  if (const char* v = getenv("F16_MATH")) G.math_mode = (!strcmp(v, "fast") || !strcmp(v, "1")) ? F16_MATH_FAST : F16_MATH_STRICT;
+  if (const char* v = getenv("F16_CLR")) G.clr_mode = (!strcmp(v, "file") || !strcmp(v, "1")) ? F16_CLR_FROM_FILE : F16_CLR_AS_BUILT;
+  if (const char* v = getenv("F16_STEP_THREADS")) G.step_threads = atoi(v);
+  if (const char* v = getenv("F16_TABLE_STAGING")) G.smem_tables = atoi(v) != 0;
+
+  int rc = upload_tables();
+  if (rc != F16_OK) return G.init_rc = rc;
+  G.ready = true;
+  return G.init_rc = F16_OK;
+}
+
+int ensure() {
+  if (G.ready) return cudaSetDevice(G.device) == cudaSuccess ? F16_OK : F16_ERR_CUDA;
+  return init_locked(nullptr, -1);
+}
+
+f16::LaunchCfg cfg(bool smem_tables) {
+  f16::LaunchCfg c;
+  c.stream = G.stream;
+  c.sm_count = G.sm_count;
+  c.step_threads = G.step_threads;
+  c.smem_tables = smem_tables;
+  c.launch_counter = &G.launches;
+  return c;
+}
+f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi}; }
+f16::BatchSel sel_of(const unsigned char* fi, int fi_default, const double* xcg, double xcg_default) {
+  return f16::BatchSel{fi, fi_default, xcg, xcg_default};
+}
+
+// host -> device staging of the optional per-aircraft selectors
+int stage_sel(const unsigned char* fi, const double* xcg, long long N, const unsigned char** d_fi, const double** d_xcg) {
+  *d_fi = nullptr;
+  *d_xcg = nullptr;
+  if (fi) {
+    CK(G.b_fi.reserve((size_t)N));
+    CK(cudaMemcpyAsync(G.b_fi.p, fi, (size_t)N, cudaMemcpyHostToDevice, G.stream));
+    *d_fi = (const unsigned char*)G.b_fi.p;
+  }
+  if (xcg) {
+    CK(G.b_xcg.reserve((size_t)N * 8));
+    CK(cudaMemcpyAsync(G.b_xcg.p, xcg, (size_t)N * 8, cudaMemcpyHostToDevice, G.stream));
+    *d_xcg = (const double*)G.b_xcg.p;
+  }
+  return F16_OK;
+}
+
+#define DISPATCH(fn, ...) (G.math_mode == F16_MATH_FAST ? f16::fast::fn(__VA_ARGS__) : f16::strict::fn(__VA_ARGS__))
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int f16_init(const char* table_path, int device) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  return init_locked(table_path, device);
+}
+
+void f16_shutdown(void) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  if (!G.ready) return;
+  cudaSetDevice(G.device);
+  cudaStreamSynchronize(G.stream);
+  for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush}) b->release();
+  if (G.d_hifi) cudaFree(G.d_hifi);
+  if (G.d_lofi) cudaFree(G.d_lofi);
+  if (G.pin) cudaFreeHost(G.pin);
+  cudaEventDestroy(G.ev0);
+  cudaEventDestroy(G.ev1);
+  cudaStreamDestroy(G.stream);
+  G = State();
+}
+
+const char* f16_last_error(void) { return t_err.c_str(); }
+int f16_last_status(void) { return G.last_status; }
+int f16_device(void) { return G.ready ? G.device : -1; }
+int f16_sm_count(void) { return G.sm_count; }
+unsigned long long f16_launch_count(void) { return G.launches; }
+void* f16_stream(void) { return (void*)G.stream; }
+
+int f16_set_math_mode(int mode) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.math_mode;
+  G.math_mode = mode == F16_MATH_FAST ? F16_MATH_FAST : F16_MATH_STRICT;
+  return prev;
+}
+
+int f16_set_clr_mode(int mode) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  int prev = G.clr_mode;
+  G.clr_mode = mode == F16_CLR_FROM_FILE ? F16_CLR_FROM_FILE : F16_CLR_AS_BUILT;
+  if (G.clr_mode != prev) {
+    cudaStreamSynchronize(G.stream);
+    rc = upload_tables();
+    if (rc != F16_OK) return rc;
+  }
+  return prev;
+}
+
+void f16_set_default_xcg(double xcg) { G.default_xcg = xcg; }
+
+int f16_set_table_staging(int mode) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.smem_tables ? 1 : 0;
+  G.smem_tables = mode != 0;
+  return prev;
+}
+
+int f16_set_step_threads(int threads) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.step_threads;
+  G.step_threads = threads;
+  return prev;
+}
+
+int f16_tables_sha256(char* out65) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  f16::payload_sha256_hex(G.payload, out65);
+  return F16_OK;
+}
+
+// ---- legacy reference ABI -------------------------------------------------------------------------------
+void f16_nlplant_xcg(const double* xu, double* xdot, int fidelity, double xcg) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  const double nan = __builtin_nan("");
+  if (ensure() != F16_OK) {
+    for (int i = 0; i < 18; i++) xdot[i] = nan;
+    G.last_status = F16_ST_NAN;
+    fprintf(stderr, "libf16_b200: Nlplant: %s\n", t_err.c_str());
+    return;
+  }
+  memcpy(G.pin, xu, 17 * sizeof(double));
+  int* st_host = reinterpret_cast<int*>(G.pin + 40);
+  int* st_dev = reinterpret_cast<int*>(G.pin_dev + 40);
+  // one aircraft: tables read through L2 (no 105 KB staging), inputs and outputs in mapped pinned memory
+  cudaError_t e = DISPATCH(launch_nlplant, cfg(false), tabs(), sel_of(nullptr, fidelity, nullptr, xcg), G.pin_dev, 1,
+                           G.pin_dev + 17, 1, 1, st_dev);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "Nlplant");
+    fprintf(stderr, "libf16_b200: Nlplant: %s\n", t_err.c_str());
+    for (int i = 0; i < 18; i++) xdot[i] = nan;
+    G.last_status = F16_ST_NAN;
+    return;
+  }
+  memcpy(xdot, G.pin + 17, 18 * sizeof(double));
+  G.last_status = *st_host;
+}
+
+void Nlplant(double* xu, double* xdot, int fidelity) { f16_nlplant_xcg(xu, xdot, fidelity, G.default_xcg); }
+
+void atmos(double alt, double vt, double* coeff) { f16_atmos(alt, vt, coeff); }
+
+void f16_atmos(double alt, double vt, double* coeff) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  const double nan = __builtin_nan("");
+  coeff[0] = coeff[1] = coeff[2] = nan;
+  if (ensure() != F16_OK) {
+    fprintf(stderr, "libf16_b200: atmos: %s\n", t_err.c_str());
+    return;
+  }
+  G.pin[48] = alt;
+  G.pin[49] = vt;
+  cudaError_t e = DISPATCH(launch_atmos, cfg(false), G.pin_dev + 48, G.pin_dev + 49, 1, G.pin_dev + 50);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "atmos");
+    fprintf(stderr, "libf16_b200: atmos: %s\n", t_err.c_str());
+    return;
+  }
+  coeff[0] = G.pin[50];
+  coeff[1] = G.pin[51];
+  coeff[2] = G.pin[52];
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------------------------
+int Nlplant_batch_dev(const double* xu_soa, long long ld_in, double* xdot_soa, long long ld_out, const unsigned char* fi,
+                      int fi_default, const double* xcg, double xcg_default, long long N, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!xu_soa || !xdot_soa)) || ld_in < N || ld_out < N) { set_err("Nlplant_batch_dev: bad argument"); return F16_ERR_ARG; }
+  CK(DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(fi, fi_default, xcg, xcg_default), xu_soa,
+              ld_in, xdot_soa, ld_out, N, status));
+  return F16_OK;
+}
+
+int calc_xdot_batch_dev(const double* x_soa, long long ld_x, const double* u_soa, long long ld_u, double* xdot_soa,
+                        long long ld_out, const unsigned char* fi, int fi_default, const double* xcg, double xcg_default,
+                        long long N, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !xdot_soa)) || ld_x < N || ld_u < N || ld_out < N) { set_err("calc_xdot_batch_dev: bad argument"); return F16_ERR_ARG; }
+  CK(DISPATCH(launch_calc_xdot, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa,
+              ld_x, u_soa, ld_u, xdot_soa, ld_out, N, status));
+  return F16_OK;
+}
+
+int step_batch_dev(double* x_soa, long long ld_x, const double* u_soa, long long ld_u, long long N, int K, double dt,
+                   const f16_lqr_t* lqr, const unsigned char* fi, int fi_default, const double* xcg, double xcg_default,
+                   int* status, int* steps_done) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || K < 0 || (N > 0 && (!x_soa || !u_soa)) || ld_x < N || ld_u < N) { set_err("step_batch_dev: bad argument"); return F16_ERR_ARG; }
+  if (lqr && (lqr->n_sel < 0 || lqr->n_sel > 18)) { set_err("step_batch_dev: lqr.n_sel out of range"); return F16_ERR_ARG; }
+  if (lqr) for (int j = 0; j < lqr->n_sel; j++) if (lqr->sel[j] < 0 || lqr->sel[j] > 17) { set_err("step_batch_dev: lqr.sel out of range"); return F16_ERR_ARG; }
+  // tables go to shared memory whenever the launch does real work; a handful of aircraft-steps read them via L2
+  const bool smem = G.smem_tables && (N * (long long)(K > 0 ? K : 1) >= 4096);
+  CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, N, K, dt,
+              reinterpret_cast<const f16::LqrLaw*>(lqr), status, steps_done));
+  return F16_OK;
+}
+
+int linearise_batch_dev(const double* x_soa, long long ld_x, const double* u_soa, long long ld_u, long long N, double eps,
+                        int scheme, double* A, double* B, const unsigned char* fi, int fi_default, const double* xcg,
+                        double xcg_default, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || ld_x < N || ld_u < N || (scheme != 0 && scheme != 1) || !(eps > 0)) {
+    set_err("linearise_batch_dev: bad argument");
+    return F16_ERR_ARG;
+  }
+  CK(DISPATCH(launch_linearise, cfg(true), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, N,
+              eps, scheme, A, B, status));
+  return F16_OK;
+}
+
+// ---- host-pointer entry points: H2D, kernels, D2H on the library stream ---------------------------------------
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, G.stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, G.stream))
+
+int Nlplant_batch(const double* xu_soa, double* xdot_soa, const unsigned char* fi, int fi_default, const double* xcg,
+                  double xcg_default, long long N, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!xu_soa || !xdot_soa))) { set_err("Nlplant_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(17 * n * 8));
+  CK(G.b_out.reserve(18 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  H2D(G.b_in.p, xu_soa, 17 * n * 8);
+  CK(DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
+              (const double*)G.b_in.p, N, (double*)G.b_out.p, N, N, (int*)G.b_st.p));
+  D2H(xdot_soa, G.b_out.p, 18 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int calc_xdot_batch(const double* x_soa, const double* u_soa, double* xdot_soa, const unsigned char* fi, int fi_default,
+                    const double* xcg, double xcg_default, long long N, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !xdot_soa))) { set_err("calc_xdot_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(18 * n * 8));
+  CK(G.b_in2.reserve(4 * n * 8));
+  CK(G.b_out.reserve(18 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  H2D(G.b_in.p, x_soa, 18 * n * 8);
+  H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  CK(DISPATCH(launch_calc_xdot, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
+              (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N, (double*)G.b_out.p, N, N, (int*)G.b_st.p));
+  D2H(xdot_soa, G.b_out.p, 18 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int step_batch(double* x_soa, const double* u_soa, long long N, int K, double dt, const f16_lqr_t* lqr,
+               const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, int* status,
+               int* steps_done) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || K < 0 || (N > 0 && (!x_soa || !u_soa))) { set_err("step_batch: bad argument"); return F16_ERR_ARG; }
+  if (lqr && (lqr->n_sel < 0 || lqr->n_sel > 18)) { set_err("step_batch: lqr.n_sel out of range"); return F16_ERR_ARG; }
+  if (lqr) for (int j = 0; j < lqr->n_sel; j++) if (lqr->sel[j] < 0 || lqr->sel[j] > 17) { set_err("step_batch: lqr.sel out of range"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(18 * n * 8));
+  CK(G.b_in2.reserve(4 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  CK(G.b_st2.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  H2D(G.b_in.p, x_soa, 18 * n * 8);
+  H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  const bool smem = G.smem_tables && (N * (long long)(K > 0 ? K : 1) >= 4096);
+  CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (double*)G.b_in.p, N,
+              (const double*)G.b_in2.p, N, N, K, dt, reinterpret_cast<const f16::LqrLaw*>(lqr), (int*)G.b_st.p,
+              (int*)G.b_st2.p));
+  D2H(x_soa, G.b_in.p, 18 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  if (steps_done) D2H(steps_done, G.b_st2.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int linearise_batch(const double* x_soa, const double* u_soa, long long N, double eps, int scheme, double* A, double* B,
+                    const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || (scheme != 0 && scheme != 1) || !(eps > 0)) {
+    set_err("linearise_batch: bad argument");
+    return F16_ERR_ARG;
+  }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(18 * n * 8));
+  CK(G.b_in2.reserve(4 * n * 8));
+  CK(G.b_a.reserve(324 * n * 8));
+  CK(G.b_b.reserve(72 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  H2D(G.b_in.p, x_soa, 18 * n * 8);
+  H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  CK(DISPATCH(launch_linearise, cfg(true), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p,
+              N, (const double*)G.b_in2.p, N, N, eps, scheme, (double*)G.b_a.p, (double*)G.b_b.p, (int*)G.b_st.p));
+  D2H(A, G.b_a.p, 324 * n * 8);
+  D2H(B, G.b_b.p, 72 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+// ---- parity probes -----------------------------------------------------------------------------------------------
+int f16_hifi_probe(const double* alpha_deg, const double* beta_deg, const double* el, long long N, double* coef, int* cells,
+                   int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N <= 0 || !alpha_deg || !beta_deg || !el || !coef || !cells) { set_err("f16_hifi_probe: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(3 * n * 8));
+  CK(G.b_out.reserve(44 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  CK(G.b_st2.reserve(8 * n * 4));
+  double* d = (double*)G.b_in.p;
+  H2D(d, alpha_deg, n * 8);
+  H2D(d + n, beta_deg, n * 8);
+  H2D(d + 2 * n, el, n * 8);
+  CK(DISPATCH(launch_hifi_probe, cfg(false), tabs(), d, d + n, d + 2 * n, N, (double*)G.b_out.p, (int*)G.b_st2.p,
+              (int*)G.b_st.p));
+  D2H(coef, G.b_out.p, 44 * n * 8);
+  D2H(cells, G.b_st2.p, 8 * n * 4);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int f16_lofi_probe(const double* alpha_deg, const double* beta_deg, const double* el, const double* dail,
+                   const double* drud, long long N, double* out) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N <= 0 || !alpha_deg || !beta_deg || !el || !dail || !drud || !out) { set_err("f16_lofi_probe: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(5 * n * 8));
+  CK(G.b_out.reserve(19 * n * 8));
+  double* d = (double*)G.b_in.p;
+  H2D(d, alpha_deg, n * 8);
+  H2D(d + n, beta_deg, n * 8);
+  H2D(d + 2 * n, el, n * 8);
+  H2D(d + 3 * n, dail, n * 8);
+  H2D(d + 4 * n, drud, n * 8);
+  CK(DISPATCH(launch_lofi_probe, cfg(false), tabs(), d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, N, (double*)G.b_out.p));
+  D2H(out, G.b_out.p, 19 * n * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int atmos_batch(const double* alt, const double* vt, long long N, double* coeff_soa) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N <= 0 || !alt || !vt || !coeff_soa) { set_err("atmos_batch: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(2 * n * 8));
+  CK(G.b_out.reserve(3 * n * 8));
+  double* d = (double*)G.b_in.p;
+  H2D(d, alt, n * 8);
+  H2D(d + n, vt, n * 8);
+  CK(DISPATCH(launch_atmos, cfg(false), d, d + n, N, (double*)G.b_out.p));
+  D2H(coeff_soa, G.b_out.p, 3 * n * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+// ---- memory / timing helpers ------------------------------------------------------------------------------------------
+void* f16_dev_alloc(unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  if (ensure() != F16_OK) return nullptr;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc"); return nullptr; }
+  return p;
+}
+void f16_dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+void* f16_host_alloc_pinned(unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  if (ensure() != F16_OK) return nullptr;
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc"); return nullptr; }
+  return p;
+}
+void f16_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int f16_memcpy_h2d(void* dst_dev, const void* src_host, unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+int f16_memcpy_d2h(void* dst_host, const void* src_dev, unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+int f16_memset_dev(void* dst_dev, int value, unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaMemsetAsync(dst_dev, value, bytes, G.stream));
+  return F16_OK;
+}
+int f16_sync(void) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+int f16_timer_start(void) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaEventRecord(G.ev0, G.stream));
+  return F16_OK;
+}
+int f16_timer_stop(float* ms) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaEventRecord(G.ev1, G.stream));
+  CK(cudaEventSynchronize(G.ev1));
+  CK(cudaEventElapsedTime(ms, G.ev0, G.ev1));
+  return F16_OK;
+}
+
+int f16_measure_fp64_peak(double ms, double* tflops) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(G.b_st.reserve(64));
+  double flops = 0;
+  float t = 0;
+  long long iters = 2000;
+  // calibrate, then run for about `ms`
+  for (int pass = 0; pass < 2; pass++) {
+    CK(cudaEventRecord(G.ev0, G.stream));
+    CK(f16::launch_dfma_peak(G.stream, G.sm_count, iters, (double*)G.b_st.p, &flops));
+    ++G.launches;
+    CK(cudaEventRecord(G.ev1, G.stream));
+    CK(cudaEventSynchronize(G.ev1));
+    CK(cudaEventElapsedTime(&t, G.ev0, G.ev1));
+    if (pass == 0) {
+      double want = ms > 1 ? ms : 1;
+      iters = (long long)(iters * want / (t > 1e-3f ? t : 1e-3f));
+      if (iters < 100) iters = 100;
+    }
+  }
+  *tflops = flops / (t * 1e-3) / 1e12;
+  return F16_OK;
+}
+
+int f16_flush_l2(void) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  const size_t bytes = 256u << 20;  // > 126 MB L2
+  CK(G.b_flush.reserve(bytes));
+  CK(cudaMemsetAsync(G.b_flush.p, 0, bytes, G.stream));
+  return F16_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,510 @@
+// f16_kernels.cu -- sm_100a kernels of the batched F-16 plant.  Compiled twice (see Makefile):
+//   -DF16_NS=strict -fmad=false   reference operation order, no FMA contraction (parity build)
+//   -DF16_NS=fast   -fmad=true    same expressions, FMA contraction allowed
+//
+// Execution model: one thread per aircraft (or per aircraft x perturbation column in linearise), the 18-element
+// state lives in registers across the K fused Euler steps of step_kernel.  The aero tables (105 KB hifi image,
+// 6 KB lofi image, f16_tables.h) are staged into shared memory once per CTA by TMA bulk copies
+// (cp.async.bulk + mbarrier) and the CTAs are persistent (grid = resident CTAs, grid-stride over aircraft).
+// FP64 pipe and shared-memory gathers bound these kernels; HBM traffic is 320 B per aircraft per launch.
+#include <stdint.h>
+
+#include "f16_kernels.cuh"
+
+#ifndef F16_NS
+#error "compile with -DF16_NS=strict or -DF16_NS=fast"
+#endif
+#define F16_THREADS 384  // derivative-only kernels: one CTA per SM, 12 warps, <= 168 registers per thread
+// step_kernel is instantiated for 256 / 384 / 512 threads per CTA (254 / 168 / 128 registers per thread, one CTA
+// per SM because of the 105 KB table image); LaunchCfg::step_threads picks one at run time.
+#define F16_LIN_WARPS 12  // linearise: 12 warps x 32 aircraft per CTA, <= 170 registers per thread
+#define F16_LIN_TILE_LD 397  // doubles per aircraft in the output tile (396 + 1: conflict-free for both phases)
+
+namespace f16 {
+namespace F16_NS {
+
+// ------------------------------------------------------------------------------------------------------
+// table staging: global -> shared with TMA bulk copies completing on one mbarrier
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int BYTES>
+__device__ __forceinline__ void stage_tables_tma(void* dst, const void* src, unsigned long long* bar) {
+  static_assert(BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  const uint32_t bar_a = smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
+    constexpr int CHUNK = 32768;
+#pragma unroll 1
+    for (int off = 0; off < BYTES; off += CHUNK) {
+      const int n = (BYTES - off) < CHUNK ? (BYTES - off) : CHUNK;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(static_cast<char*>(dst) + off)),
+          "l"(static_cast<const char*>(src) + off), "r"(n), "r"(bar_a)
+          : "memory");
+    }
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar_a), "r"(0)
+        : "memory");
+  }
+}
+
+template <int FI>
+struct Img {
+  static constexpr int DOUBLES = FI ? F16_IMG_HIFI_DOUBLES : F16_IMG_LOFI_DOUBLES;
+  static constexpr int BYTES = DOUBLES * 8;
+  static constexpr int SMEM_BYTES = BYTES + 16;  // + the mbarrier
+};
+
+extern __shared__ __align__(128) unsigned char f16_smem[];
+
+template <int FI, bool SMEM>
+__device__ __forceinline__ const double* acquire_tables(const DevTables& t) {
+  const double* g = FI ? t.hifi : t.lofi;
+  if (!SMEM) return g;
+  stage_tables_tma<Img<FI>::BYTES>(f16_smem, g, reinterpret_cast<unsigned long long*>(f16_smem + Img<FI>::BYTES));
+  return reinterpret_cast<const double*>(f16_smem);
+}
+
+// which aircraft does the FI instantiation own?  (per-aircraft flags other than 0/1 are reported by FI == 1)
+template <int FI>
+__device__ __forceinline__ int owns(const BatchSel& s, long long n) {
+  const int f = s.fi ? (int)s.fi[n] : s.fi_default;
+  if (f == FI) return 1;
+  if (FI == 1 && f != 0) return -1;
+  return 0;
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ------------------------------------------------------------------------------------------------------
+// Nlplant_batch: xu [17][N] -> xdot [18][N]
+// ------------------------------------------------------------------------------------------------------
+template <int FI, bool SMEM>
+__global__ void __launch_bounds__(F16_THREADS, 1)
+nlplant_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ xu_g, long long ld_in, double* __restrict__ xd_g,
+               long long ld_out, long long N, int* __restrict__ status) {
+  const double* img = acquire_tables<FI, SMEM>(tabs);
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    double xu[17], xd[18];
+#pragma unroll
+    for (int i = 0; i < 17; i++) xu[i] = xu_g[i * ld_in + n];
+    unsigned st = ST_FIDELITY;
+    if (own == 1) st = nlplant_eval<FI>(img, xu, sel.xcg ? sel.xcg[n] : sel.xcg_default, xd);
+    if (st) {
+#pragma unroll
+      for (int i = 0; i < 18; i++) xd[i] = qnan();
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) xd_g[i * ld_out + n] = xd[i];
+    if (status) status[n] = (int)st;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// calc_xdot_batch: env.py::_calc_xdot for N aircraft
+// ------------------------------------------------------------------------------------------------------
+template <int FI, bool SMEM>
+__global__ void __launch_bounds__(F16_THREADS, 1)
+calc_xdot_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x,
+                 const double* __restrict__ u_g, long long ld_u, double* __restrict__ xd_g, long long ld_out,
+                 long long N, int* __restrict__ status) {
+  const double* img = acquire_tables<FI, SMEM>(tabs);
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    double x[18], u[4], xd[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = u_g[i * ld_u + n];
+    unsigned st = ST_FIDELITY;
+    if (own == 1) st = calc_xdot<FI>(img, x, u, sel.xcg ? sel.xcg[n] : sel.xcg_default, xd);
+    if (st) {
+#pragma unroll
+      for (int i = 0; i < 18; i++) xd[i] = qnan();
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) xd_g[i * ld_out + n] = xd[i];
+    if (status) status[n] = (int)st;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// step_batch: K fused explicit-Euler steps of env.py::step, state in registers, optional fused LQR law
+// ------------------------------------------------------------------------------------------------------
+__constant__ LqrLaw c_lqr;
+
+template <int FI, bool SMEM, bool LQR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g,
+            long long ld_u, long long N, int K, double dt, int* __restrict__ status, int* __restrict__ steps_done) {
+  const double* img = acquire_tables<FI, SMEM>(tabs);
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    if (own < 0) {
+      if (status) status[n] = (int)ST_FIDELITY;
+      if (steps_done) steps_done[n] = 0;
+      continue;
+    }
+    double x[18], u_in[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
+    const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+    unsigned st = 0;
+    int k = 0;
+#pragma unroll 1
+    for (; k < K; k++) {
+      st = step_bounds(x, u_in);  // env.py:117 -- the reference exit()s here; we freeze this aircraft
+      if (st) break;
+      double u[4], xd[18];
+      if (LQR) {
+        lqr_action(c_lqr, x, u_in, u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = u_in[i];
+      }
+      st = calc_xdot<FI>(img, x, u, xcg, xd);
+      if (st) break;
+#pragma unroll
+      for (int i = 0; i < 18; i++) x[i] = x[i] + xd[i] * dt;  // env.py:126
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (status) status[n] = (int)st;
+    if (steps_done) steps_done[n] = k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// linearise_batch: finite-difference A [18x18], B [18x4] of _calc_xdot (env.py:294-342).
+// CTA = 32 aircraft x F16_LIN_WARPS warps; warp w evaluates perturbation columns w, w+W, ... for the CTA's 32
+// aircraft (lane = aircraft, so every warp is column-uniform), results go to a padded shared tile and are
+// written out as contiguous [aircraft][18][18] / [aircraft][18][4] runs.
+// ------------------------------------------------------------------------------------------------------
+template <int FI>
+struct LinSmem {
+  static constexpr int TILE_OFF = (Img<FI>::SMEM_BYTES + 127) / 128 * 128;
+  static constexpr int TILE_BYTES = 32 * F16_LIN_TILE_LD * 8;
+  static constexpr int BASE_OFF = TILE_OFF + TILE_BYTES;  // f(x,u) per aircraft: [32][19]
+  static constexpr int BASE_BYTES = 32 * 19 * 8;
+  static constexpr int STAT_OFF = BASE_OFF + BASE_BYTES;
+  static constexpr int TOTAL = STAT_OFF + 32 * 4;
+};
+
+template <int FI>
+__global__ void __launch_bounds__(F16_LIN_WARPS * 32, 1)
+linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x,
+                 const double* __restrict__ u_g, long long ld_u, long long N, double eps, int scheme,
+                 double* __restrict__ A_g, double* __restrict__ B_g, int* __restrict__ status) {
+  const double* img = acquire_tables<FI, true>(tabs);
+  double* tile = reinterpret_cast<double*>(f16_smem + LinSmem<FI>::TILE_OFF);
+  double* base = reinterpret_cast<double*>(f16_smem + LinSmem<FI>::BASE_OFF);
+  int* stat = reinterpret_cast<int*>(f16_smem + LinSmem<FI>::STAT_OFF);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_groups = (N + 31) / 32;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long n = grp * 32 + lane;
+    const bool live = n < N;
+    const int own = live ? owns<FI>(sel, n) : 0;
+    if (threadIdx.x < 32) stat[threadIdx.x] = (own < 0) ? (int)ST_FIDELITY : 0;
+    __syncthreads();
+    double x0[18], u0[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x0[i] = live ? x_g[i * ld_x + n] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) u0[i] = live ? u_g[i * ld_u + n] : 0.0;
+    const double xcg = (live && sel.xcg) ? sel.xcg[n] : sel.xcg_default;
+    // columns 0..21 perturb x[0..17], u[0..3]; forward also needs column 22 = the unperturbed point
+    const int ncol = scheme == 0 ? 23 : 22;
+    for (int c = warp; c < ncol; c += F16_LIN_WARPS) {
+      if (own != 1) continue;
+      double x[18], u[4], fp[18], fm[18];
+      unsigned st = 0;
+#pragma unroll
+      for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? eps : 0.0);
+#pragma unroll
+      for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? eps : 0.0);
+      st |= calc_xdot<FI>(img, x, u, xcg, fp);
+      if (scheme != 0) {
+#pragma unroll
+        for (int i = 0; i < 18; i++) x[i] = x0[i] - (i == c ? eps : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = u0[i] - (i + 18 == c ? eps : 0.0);
+        st |= calc_xdot<FI>(img, x, u, xcg, fm);
+      }
+      if (st) {
+        atomicOr(&stat[lane], (int)st);
+#pragma unroll
+        for (int i = 0; i < 18; i++) fp[i] = qnan();
+      }
+      if (c == 22) {
+#pragma unroll
+        for (int r = 0; r < 18; r++) base[lane * 19 + r] = fp[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 18; r++) {
+          const double v = scheme == 0 ? fp[r] : (fp[r] - fm[r]) / (2 * eps);
+          const int k = c < 18 ? r * 18 + c : 324 + r * 4 + (c - 18);
+          tile[lane * F16_LIN_TILE_LD + k] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // write-out: 32 aircraft x 324 (A) and x 72 (B) contiguous doubles
+    const long long n0 = grp * 32;
+    const int n_here = (int)((N - n0) < 32 ? (N - n0) : 32);
+    for (int e = threadIdx.x; e < n_here * 324; e += blockDim.x) {
+      const int a = e / 324, k = e - a * 324;
+      if (owns<FI>(sel, n0 + a) == 0) continue;
+      double v = tile[a * F16_LIN_TILE_LD + k];
+      if (scheme == 0) v = (v - base[a * 19 + k / 18]) / eps;  // env.py:330
+      if (stat[a] & (int)ST_FIDELITY) v = qnan();
+      A_g[n0 * 324 + e] = v;
+    }
+    for (int e = threadIdx.x; e < n_here * 72; e += blockDim.x) {
+      const int a = e / 72, k = e - a * 72;
+      if (owns<FI>(sel, n0 + a) == 0) continue;
+      double v = tile[a * F16_LIN_TILE_LD + 324 + k];
+      if (scheme == 0) v = (v - base[a * 19 + k / 4]) / eps;  // env.py:339
+      if (stat[a] & (int)ST_FIDELITY) v = qnan();
+      B_g[n0 * 72 + e] = v;
+    }
+    if (status && threadIdx.x < n_here && owns<FI>(sel, n0 + threadIdx.x) != 0) status[n0 + threadIdx.x] = stat[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// parity probes
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hifi_probe_kernel(DevTables tabs, const double* __restrict__ alpha, const double* __restrict__ beta,
+                  const double* __restrict__ el, long long N, double* __restrict__ coef, int* __restrict__ cells,
+                  int* __restrict__ status) {
+  const double* img = tabs.hifi;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const double a = alpha[n], b = beta[n], e = el[n];
+    const unsigned st = hifi_envelope(a, b, e);
+    double o[44];
+    int cl[8];
+    if (st) {
+#pragma unroll
+      for (int i = 0; i < 44; i++) o[i] = qnan();
+#pragma unroll
+      for (int i = 0; i < 8; i++) cl[i] = -1;
+    } else {
+      const HifiLoc L = hifi_locate(img, a, b, e);
+      Coef c;
+      hifi_coefs(img, L, c);
+      o[0] = c.Cx; o[1] = c.Cz; o[2] = c.Cm; o[3] = c.Cy; o[4] = c.Cn; o[5] = c.Cl;
+      o[6] = c.Cxq; o[7] = c.Cyr; o[8] = c.Cyp; o[9] = c.Czq; o[10] = c.Clr; o[11] = c.Clp; o[12] = c.Cmq;
+      o[13] = c.Cnr; o[14] = c.Cnp;
+      o[15] = c.dCx_lef; o[16] = c.dCz_lef; o[17] = c.dCm_lef; o[18] = c.dCy_lef; o[19] = c.dCn_lef; o[20] = c.dCl_lef;
+      o[21] = c.dCxq_lef; o[22] = c.dCyr_lef; o[23] = c.dCyp_lef; o[24] = c.dCzq_lef; o[25] = c.dClr_lef;
+      o[26] = c.dClp_lef; o[27] = c.dCmq_lef; o[28] = c.dCnr_lef; o[29] = c.dCnp_lef;
+      o[30] = c.dCy_r30; o[31] = c.dCn_r30; o[32] = c.dCl_r30;
+      o[33] = c.dCy_a20; o[34] = c.dCy_a20_lef; o[35] = c.dCn_a20; o[36] = c.dCn_a20_lef; o[37] = c.dCl_a20;
+      o[38] = c.dCl_a20_lef;
+      o[39] = c.dCnbeta; o[40] = c.dClbeta; o[41] = c.dCm; o[42] = c.eta_el; o[43] = c.dCm_ds;
+      ref_cell(img + F16_IMG_A, L.a, a, cl[0], cl[1]);
+      ref_cell(img + F16_IMG_B, L.b, b, cl[2], cl[3]);
+      ref_cell(img + F16_IMG_D1, L.d1, e, cl[4], cl[5]);
+      ref_cell(img + F16_IMG_D2, L.d2, e, cl[6], cl[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 44; i++) coef[i * N + n] = o[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cells[i * N + n] = cl[i];
+    if (status) status[n] = (int)st;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lofi_probe_kernel(DevTables tabs, const double* __restrict__ alpha, const double* __restrict__ beta,
+                  const double* __restrict__ el, const double* __restrict__ dail, const double* __restrict__ drud,
+                  long long N, double* __restrict__ out) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    Coef c;
+    lofi_coefs(tabs.lofi, alpha[n], beta[n], el[n], dail[n], drud[n], c);
+    const double o[19] = {c.Cxq, c.Cyr, c.Cyp, c.Czq, c.Clr, c.Clp, c.Cmq, c.Cnr, c.Cnp, c.dCl_a20,
+                          c.dCl_r30, c.dCn_a20, c.dCn_r30, c.Cl, c.Cn, c.Cx, c.Cm, c.Cz, c.Cy};
+#pragma unroll
+    for (int i = 0; i < 19; i++) out[i * N + n] = o[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+atmos_kernel(const double* __restrict__ alt, const double* __restrict__ vt, long long N, double* __restrict__ coeff) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const Atmos a = atmos_eval(alt[n], vt[n]);
+    coeff[n] = a.mach;
+    coeff[N + n] = a.qbar;
+    coeff[2 * N + n] = a.ps;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------
+static int grid_for(long long work_items, int per_block, int resident) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > resident) b = resident;
+  return (int)b;
+}
+
+template <typename Kern>
+static cudaError_t prepare(Kern kern, int threads, int smem, int sm_count, int* resident) {
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  *resident = per_sm * sm_count;
+  return cudaSuccess;
+}
+
+static bool wants(const BatchSel& s, int FI) { return s.fi != nullptr || s.fi_default == FI || (FI == 1 && s.fi_default != 0); }
+
+// persistent launch: grid = min(ceil(items / per_block), resident CTAs)
+template <typename Kern, typename... Args>
+static cudaError_t launch_persistent(const LaunchCfg& cfg, Kern kern, int threads, int smem, long long items,
+                                     int per_block, Args... args) {
+  int resident = 0;
+  cudaError_t e = prepare(kern, threads, smem, cfg.sm_count, &resident);
+  if (e != cudaSuccess) return e;
+  kern<<<grid_for(items, per_block, resident), threads, smem, cfg.stream>>>(args...);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
+template <int FI>
+static int table_smem(bool smem_tables) { return smem_tables ? Img<FI>::SMEM_BYTES : 0; }
+
+cudaError_t launch_nlplant(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* xu,
+                           long long ld_in, double* xdot, long long ld_out, long long N, int* status) {
+  if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  const bool s = cfg.smem_tables;
+  if (wants(sel, 1))
+    e = launch_persistent(cfg, s ? nlplant_kernel<1, true> : nlplant_kernel<1, false>, F16_THREADS, table_smem<1>(s), N,
+                          F16_THREADS, tabs, sel, xu, ld_in, xdot, ld_out, N, status);
+  if (e == cudaSuccess && wants(sel, 0))
+    e = launch_persistent(cfg, s ? nlplant_kernel<0, true> : nlplant_kernel<0, false>, F16_THREADS, table_smem<0>(s), N,
+                          F16_THREADS, tabs, sel, xu, ld_in, xdot, ld_out, N, status);
+  return e;
+}
+
+cudaError_t launch_calc_xdot(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* x,
+                             long long ld_x, const double* u, long long ld_u, double* xdot, long long ld_out,
+                             long long N, int* status) {
+  if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  const bool s = cfg.smem_tables;
+  if (wants(sel, 1))
+    e = launch_persistent(cfg, s ? calc_xdot_kernel<1, true> : calc_xdot_kernel<1, false>, F16_THREADS,
+                          table_smem<1>(s), N, F16_THREADS, tabs, sel, x, ld_x, u, ld_u, xdot, ld_out, N, status);
+  if (e == cudaSuccess && wants(sel, 0))
+    e = launch_persistent(cfg, s ? calc_xdot_kernel<0, true> : calc_xdot_kernel<0, false>, F16_THREADS,
+                          table_smem<0>(s), N, F16_THREADS, tabs, sel, x, ld_x, u, ld_u, xdot, ld_out, N, status);
+  return e;
+}
+
+using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
+                          int*);
+
+template <int FI, bool LQR>
+static StepKern pick_step(bool smem_tables, int& threads) {
+  if (!smem_tables) { threads = 256; return step_kernel<FI, false, LQR, 256>; }
+  if (threads <= 256) { threads = 256; return step_kernel<FI, true, LQR, 256>; }
+  if (threads <= 384) { threads = 384; return step_kernel<FI, true, LQR, 384>; }
+  threads = 512;
+  return step_kernel<FI, true, LQR, 512>;
+}
+
+cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x,
+                        const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
+                        int* status, int* steps_done) {
+  if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (lqr_host) {
+    e = cudaMemcpyToSymbolAsync(c_lqr, lqr_host, sizeof(LqrLaw), 0, cudaMemcpyHostToDevice, cfg.stream);
+    if (e != cudaSuccess) return e;
+  }
+  for (int FI = 1; FI >= 0 && e == cudaSuccess; FI--) {
+    if (!wants(sel, FI)) continue;
+    int threads = cfg.step_threads;
+    StepKern k = FI ? (lqr_host ? pick_step<1, true>(cfg.smem_tables, threads) : pick_step<1, false>(cfg.smem_tables, threads))
+                    : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
+    const int smem = FI ? table_smem<1>(cfg.smem_tables) : table_smem<0>(cfg.smem_tables);
+    e = launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+  }
+  return e;
+}
+
+cudaError_t launch_linearise(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* x,
+                             long long ld_x, const double* u, long long ld_u, long long N, double eps, int scheme,
+                             double* A, double* B, int* status) {
+  if (N <= 0) return cudaSuccess;
+  const long long groups = (N + 31) / 32;
+  const int threads = F16_LIN_WARPS * 32;
+  cudaError_t e = cudaSuccess;
+  if (wants(sel, 1))
+    e = launch_persistent(cfg, linearise_kernel<1>, threads, LinSmem<1>::TOTAL, groups, 1, tabs, sel, x, ld_x, u, ld_u,
+                          N, eps, scheme, A, B, status);
+  if (e == cudaSuccess && wants(sel, 0))
+    e = launch_persistent(cfg, linearise_kernel<0>, threads, LinSmem<0>::TOTAL, groups, 1, tabs, sel, x, ld_x, u, ld_u,
+                          N, eps, scheme, A, B, status);
+  return e;
+}
+
+cudaError_t launch_hifi_probe(const LaunchCfg& cfg, const DevTables& tabs, const double* alpha, const double* beta,
+                              const double* el, long long N, double* coef, int* cells, int* status) {
+  if (N <= 0) return cudaSuccess;
+  hifi_probe_kernel<<<grid_for(N, 256, cfg.sm_count * 8), 256, 0, cfg.stream>>>(tabs, alpha, beta, el, N, coef, cells,
+                                                                                status);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lofi_probe(const LaunchCfg& cfg, const DevTables& tabs, const double* alpha, const double* beta,
+                              const double* el, const double* dail, const double* drud, long long N, double* out) {
+  if (N <= 0) return cudaSuccess;
+  lofi_probe_kernel<<<grid_for(N, 256, cfg.sm_count * 8), 256, 0, cfg.stream>>>(tabs, alpha, beta, el, dail, drud, N,
+                                                                                out);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_atmos(const LaunchCfg& cfg, const double* alt, const double* vt, long long N, double* coeff) {
+  if (N <= 0) return cudaSuccess;
+  atmos_kernel<<<grid_for(N, 256, cfg.sm_count * 8), 256, 0, cfg.stream>>>(alt, vt, N, coeff);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
+}  // namespace F16_NS
+}  // namespace f16

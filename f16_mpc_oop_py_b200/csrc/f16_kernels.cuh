@@ -1,0 +1,58 @@
+// f16_kernels.cuh -- launch interface between the C ABI (f16_api.cu) and the kernel translation unit, which is
+// compiled twice: f16_kernels.cu with -fmad=false as namespace f16::strict and with -fmad=true as f16::fast.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "f16_model.cuh"
+
+namespace f16 {
+
+struct DevTables {
+  const double* hifi;  // F16_IMG_HIFI_DOUBLES, 16-byte aligned
+  const double* lofi;  // F16_IMG_LOFI_DOUBLES
+};
+
+struct BatchSel {           // which aircraft run which model
+  const unsigned char* fi;  // per-aircraft fidelity (device) or nullptr
+  int fi_default;
+  const double* xcg;  // per-aircraft xcg (device) or nullptr
+  double xcg_default;
+};
+
+struct LaunchCfg {
+  cudaStream_t stream;
+  int sm_count;
+  int step_threads;  // CTA size of step_kernel: 256, 384 or 512
+  bool smem_tables;  // stage tables in shared memory with TMA bulk copies (default) or read them through L1/L2
+  unsigned long long* launch_counter;
+};
+
+#define F16_DECLARE_LAUNCHERS                                                                                        \
+  cudaError_t launch_nlplant(const LaunchCfg&, const DevTables&, const BatchSel&, const double* xu, long long ld_in,  \
+                             double* xdot, long long ld_out, long long N, int* status);                              \
+  cudaError_t launch_calc_xdot(const LaunchCfg&, const DevTables&, const BatchSel&, const double* x, long long ld_x,  \
+                               const double* u, long long ld_u, double* xdot, long long ld_out, long long N,         \
+                               int* status);                                                                         \
+  cudaError_t launch_step(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,            \
+                          const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,    \
+                          int* status, int* steps_done);                                                             \
+  cudaError_t launch_linearise(const LaunchCfg&, const DevTables&, const BatchSel&, const double* x, long long ld_x,  \
+                               const double* u, long long ld_u, long long N, double eps, int scheme, double* A,      \
+                               double* B, int* status);                                                              \
+  cudaError_t launch_hifi_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta,         \
+                                const double* el, long long N, double* coef, int* cells, int* status);              \
+  cudaError_t launch_lofi_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta,         \
+                                const double* el, const double* dail, const double* drud, long long N, double* out); \
+  cudaError_t launch_atmos(const LaunchCfg&, const double* alt, const double* vt, long long N, double* coeff);
+
+namespace strict {
+F16_DECLARE_LAUNCHERS
+}
+namespace fast {
+F16_DECLARE_LAUNCHERS
+}
+
+// FP64 FMA micro-benchmark (f16_peak.cu): returns flops executed
+cudaError_t launch_dfma_peak(cudaStream_t stream, int sm_count, long long iters, double* sink, double* flops);
+
+}  // namespace f16

@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference's plant interface (env.py::F16) over the batched C ABI.
+
+`F16Batch` keeps the reference's method names and argument meaning -- `_calc_xdot(x, u)`, `step(action)`,
+`reset()`, `get_obs(x, u)`, `linearise(x, u)` -- for N aircraft at once, with states as SoA arrays [18][N].
+Every method is a call into libf16_b200.so (CUDA); nothing is computed in Python.
+
+Differences from env.py that a user sees:
+  * leaving the envelope does not `exit()` the process (env.py:117-124): the aircraft is flagged in `status`
+    and frozen at the violating state;
+  * `linearise` offers scheme='forward' (env.py:319-340) and 'central';
+  * xcg and fidelity are arguments (scalars or per-aircraft arrays) instead of a choice of .so file
+    (parameters.py:108-114) and a dataclass field.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import parameters as P
+from ._lib import LqrLaw, check, lib
+
+
+def _c(a, dtype=np.float64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _sel(fi, xcg, n):
+    """(fi array or None, default fi, xcg array or None, default xcg) for the C ABI."""
+    fi_arr = xcg_arr = None
+    fi_def, xcg_def = 1, 0.25
+    if np.ndim(fi) == 0:
+        fi_def = int(fi)
+    else:
+        fi_arr = _c(fi, np.uint8)
+        assert fi_arr.shape == (n,)
+    if np.ndim(xcg) == 0:
+        xcg_def = float(xcg)
+    else:
+        xcg_arr = _c(xcg)
+        assert xcg_arr.shape == (n,)
+    return fi_arr, fi_def, xcg_arr, xcg_def
+
+
+def make_lqr(K, sel, x_ref, u0, rows):
+    """f16_lqr_t for u[rows] = u0[rows] - K (x[sel] - x_ref); K is [len(rows)][len(sel)]."""
+    law = LqrLaw()
+    K = np.atleast_2d(np.asarray(K, dtype=np.float64))
+    assert K.shape == (len(rows), len(sel)) and len(sel) <= 18
+    law.n_sel = len(sel)
+    law.row_mask = 0
+    for j, s in enumerate(sel):
+        law.sel[j] = int(s)
+        law.x_ref[j] = float(x_ref[j])
+    for i, r in enumerate(rows):
+        law.row_mask |= 1 << int(r)
+        for j in range(len(sel)):
+            law.K[r][j] = float(K[i, j])
+    for r in range(4):
+        law.u0[r] = float(u0[r])
+    return law
+
+
+def nlplant(xu, fi=1, xcg=0.25):
+    """Nlplant_batch: xu [17][N] -> (xdot [18][N], status [N])  (C/nlplant.c:23-457 for N aircraft)."""
+    xu = _c(xu)
+    assert xu.ndim == 2 and xu.shape[0] == 17
+    n = xu.shape[1]
+    fa, fd, xa, xd = _sel(fi, xcg, n)
+    out = np.empty((18, n))
+    st = np.zeros(n, dtype=np.int32)
+    check(lib.Nlplant_batch(_p(xu), _p(out), None if fa is None else fa.ctypes.data_as(_lib.c_ubp), fd,
+                            None if xa is None else xa.ctypes.data_as(_lib.c_dp), xd, n, _p(st)), "Nlplant_batch")
+    return out, st
+
+
+def atmos(alt, vt):
+    """atmos_batch: -> [3][N] = mach, qbar, ps (C/nlplant.c:467-490)."""
+    alt, vt = _c(np.atleast_1d(alt)), _c(np.atleast_1d(vt))
+    out = np.empty((3, alt.size))
+    check(lib.atmos_batch(_p(alt), _p(vt), alt.size, _p(out)), "atmos_batch")
+    return out
+
+
+class F16Batch:
+    """N independent F-16s behind the reference's F16 interface (env.py:29-342)."""
+
+    def __init__(self, x0, u0, fi_flag=P.fi_flag, xcg=0.25, dt=P.dt):
+        self.initial_x = _c(x0).reshape(18, -1).copy()
+        self.initial_u = _c(u0).reshape(4, -1).copy()
+        self.n = self.initial_x.shape[1]
+        assert self.initial_u.shape[1] == self.n
+        self.fi_flag, self.xcg, self.dt = fi_flag, xcg, dt
+        self._selargs = _sel(fi_flag, xcg, self.n)
+        self.reset()
+
+    def _sel_c(self):
+        fa, fd, xa, xd = self._selargs
+        return (None if fa is None else fa.ctypes.data_as(_lib.c_ubp), fd,
+                None if xa is None else xa.ctypes.data_as(_lib.c_dp), xd)
+
+    # env.py:132-135
+    def reset(self):
+        self.x = self.initial_x.copy()
+        self.u = self.initial_u.copy()
+        self.status = np.zeros(self.n, dtype=np.int32)
+        self.steps_done = np.zeros(self.n, dtype=np.int32)
+        return self.get_obs(self.x, self.u)
+
+    # env.py:137-150
+    def get_obs(self, x, u):
+        return np.asarray(x)[P.obs_x_idx]
+
+    # env.py:65-103
+    def _calc_xdot(self, x, u):
+        x, u = _c(x).reshape(18, -1), _c(u).reshape(4, -1)
+        n = x.shape[1]
+        out = np.empty((18, n))
+        st = np.zeros(n, dtype=np.int32)
+        check(lib.calc_xdot_batch(_p(x), _p(u), _p(out), *self._sel_c(), n, _p(st)), "calc_xdot_batch")
+        self.last_status = st
+        return out
+
+    # env.py:105-130: `action` = [T, dh, da, dr] demands, [4] or [4][N]; K fused Euler steps per call
+    def step(self, action=None, K=1, lqr=None):
+        if action is not None:
+            a = _c(action)
+            self.u = np.ascontiguousarray(np.broadcast_to(a.reshape(4, -1), (4, self.n)))
+        law = ctypes.byref(lqr) if lqr is not None else None
+        check(lib.step_batch(_p(self.x), _p(self.u), self.n, int(K), float(self.dt), law, *self._sel_c(),
+                             _p(self.status), _p(self.steps_done)), "step_batch")
+        reward, isdone = 1, self.status != 0
+        info = {'fidelity': 'high' if np.all(np.asarray(self.fi_flag) == 1) else 'mixed/low', 'status': self.status}
+        return self.get_obs(self.x, self.u), reward, isdone, info
+
+    # env.py:294-342
+    def linearise(self, x, u, scheme='forward', eps=1e-5):
+        x, u = _c(x).reshape(18, -1), _c(u).reshape(4, -1)
+        n = x.shape[1]
+        A = np.empty((n, 18, 18))
+        B = np.empty((n, 18, 4))
+        st = np.zeros(n, dtype=np.int32)
+        sch = {'forward': _lib.FD_FORWARD, 'central': _lib.FD_CENTRAL}[scheme]
+        check(lib.linearise_batch(_p(x), _p(u), n, float(eps), sch, _p(A), _p(B), *self._sel_c(), _p(st)),
+              "linearise_batch")
+        self.last_status = st
+        # C, D of env.py:311-340 are selector matrices of the observed states
+        C = np.zeros((len(P.obs_x_idx), 18))
+        C[np.arange(len(P.obs_x_idx)), P.obs_x_idx] = 1.0
+        D = np.zeros((len(P.obs_x_idx), 4))
+        return A, B, C, D

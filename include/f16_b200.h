@@ -1,0 +1,170 @@
+/*
+ * f16_b200.h -- C ABI of libf16_b200.so, the B200 (sm_100a) batched F-16 plant.
+ *
+ * Drop-in boundary.  The reference project (johnviljoen/f16_mpc_oop_py) loads `C/nlplant_xcg25.so` or
+ * `C/nlplant_xcg35.so` with ctypes.CDLL (parameters.py:108-114) and calls exactly two symbols:
+ *     Nlplant(xu*, xdot*, int)   env.py:100, env.py:187      (C/nlplant.c:14,23)
+ *     atmos(alt, vt, coeff*)     utils.py:291                (C/nlplant.c:8,467)
+ * Both are exported here with the reference's signatures; the batched entry points below are new and take
+ * struct-of-arrays buffers.  Plain pointers and sizes only; the caller owns every buffer; nothing is retained.
+ *
+ * There is no CPU implementation behind any of these calls: every one of them runs the CUDA kernels of this
+ * library and returns F16_ERR_CUDA (or writes NaN for the two void legacy symbols) if no B200 is usable.
+ *
+ * Conventions
+ *   state  x[18] = {npos,epos,h,phi,theta,psi,V,alpha,beta,p,q,r,T,dh,da,dr,lf2,lf1}   (parameters.py:116)
+ *   input  u[4]  = {T,dh,da,dr}                                                          (parameters.py:117)
+ *   xu[17]       = x[0:17] as Nlplant reads it (C/nlplant.c:76-114; xu[16] = lef)
+ *   SoA layout   plane i of an [M][N] array starts at base + i*ld (ld = N for the host entry points)
+ *   fidelity     1 = hifi (Nguyen tables), 0 = lofi (Stevens-Lewis)                      (C/nlplant.c:183,245)
+ *   xcg          centre of gravity as a fraction of cbar; the reference compiles 0.25 or 0.35 in (C/nlplant.c:34)
+ */
+#ifndef F16_B200_H
+#define F16_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ------------------------------------------------------------------------------ */
+#define F16_OK 0
+#define F16_ERR_CUDA (-1)    /* CUDA runtime error or no usable device; see f16_last_error() */
+#define F16_ERR_TABLES (-2)  /* aero tables not found or corrupt */
+#define F16_ERR_ARG (-3)     /* bad argument */
+#define F16_ERR_NOINIT (-4)  /* internal: initialisation failed earlier */
+
+/* ---- per-aircraft status word (int32, sticky within one call) ------------------------------------
+ * The reference's behaviour in these cases is exit() (env.py:117-124) or undefined (mexndinterp.c:121-123);
+ * here the aircraft is flagged, Nlplant_batch writes NaN derivatives and step_batch freezes the state at
+ * the first violating step. */
+#define F16_ST_BOUND(i) (1 << (i)) /* bits 0..17: state i outside parameters.py:122-123 (compared raw, as there) */
+#define F16_ST_ALPHA (1 << 18)     /* alpha outside the tables: hifi [-20,45] deg */
+#define F16_ST_BETA (1 << 19)      /* beta outside [-30,30] deg */
+#define F16_ST_DELE (1 << 20)      /* elevator outside [-25,25] deg (hifi) */
+#define F16_ST_NAN (1 << 21)       /* NaN in a state or input */
+#define F16_ST_FIDELITY (1 << 22)  /* fidelity flag neither 0 nor 1 */
+
+/* ---- arithmetic mode ---------------------------------------------------------------------------- */
+#define F16_MATH_STRICT 0 /* reference operation order, no FMA contraction: the parity build */
+#define F16_MATH_FAST 1   /* same expressions with FMA contraction (|diff| <= 1e-13 scaled) */
+
+/* ---- CLr table quirk ---------------------------------------------------------------------------
+ * The reference never loads CL1320_ALPHA1_606.dat (hifi_F16_AeroData.c:965-972: the fscanf loop is the
+ * body of `if(fp==NULL)`), so its binaries compute with CLr = 0.  Default: as built. */
+#define F16_CLR_AS_BUILT 0
+#define F16_CLR_FROM_FILE 1
+
+/* ---- finite-difference schemes of linearise_batch ------------------------------------------------ */
+#define F16_FD_FORWARD 0 /* (f(x+eps e_i) - f(x))/eps, env.py:319-340 */
+#define F16_FD_CENTRAL 1 /* (f(x+eps e_i) - f(x-eps e_i))/(2 eps) */
+
+/* ---- closed-loop law fused into step_batch -------------------------------------------------------
+ * For every input row r with bit r of row_mask set:
+ *     u[r] = u0[r] - sum_{j<n_sel} K[r][j] * (x[sel[j]] - x_ref[j])        (accumulated in j order)
+ * other rows keep the open-loop input.  With sel = parameters.py mpc_states indices [3,4,7,8,9,10,11,17,16],
+ * rows {1,2,3} and K from env.py:344-358 this is test_env.py:294 (u = u0 - K(x - x_ref)); env.py:360-371
+ * (x_ref = x except p,q,r) is the same law with only the p,q,r columns of K non-zero. */
+typedef struct f16_lqr_t {
+  int n_sel;
+  int row_mask;
+  int sel[18];
+  double K[4][18];
+  double x_ref[18];
+  double u0[4];
+} f16_lqr_t;
+
+/* ---- legacy symbols: the reference ABI ------------------------------------------------------------ */
+/* Replaces C/nlplant.c:23-457.  Reads xu[0..16], writes xdot[0..17] ([12..14] = nx,ny,nz, [15..17] = mach,
+ * qbar,ps).  xcg comes from f16_set_default_xcg (the C/nlplant_xcg25.so / xcg35.so shims fix it).  Outside
+ * the table envelope the reference is undefined; this writes NaN and sets f16_last_status(). */
+void Nlplant(double *xu, double *xdot, int fidelity);
+/* Replaces C/nlplant.c:467-490.  coeff[0..2] = mach, qbar, ps. */
+void atmos(double alt, double vt, double *coeff);
+/* Same as Nlplant with an explicit xcg, and atmos under a second name: what the two drop-in shim libraries
+ * (C/nlplant_xcg25.so, C/nlplant_xcg35.so, csrc/f16_shim.c) forward to. */
+void f16_nlplant_xcg(const double *xu, double *xdot, int fidelity, double xcg);
+void f16_atmos(double alt, double vt, double *coeff);
+
+/* ---- library state --------------------------------------------------------------------------------- */
+/* Idempotent.  table_path: the packed blob (f16_aero_v1.bin), or a directory holding the reference's C/*.dat
+ * files, or NULL to search $F16_TABLE_PATH, <lib dir>/../data/f16_aero_v1.bin, ./C/.  device: CUDA ordinal,
+ * or -1 for $F16_DEVICE / $LOCAL_RANK / 0.  Called implicitly (NULL, -1) by every other entry point. */
+int f16_init(const char *table_path, int device);
+void f16_shutdown(void);
+const char *f16_last_error(void);
+int f16_last_status(void);            /* status word of the last legacy Nlplant call */
+int f16_device(void);                 /* CUDA ordinal in use, -1 before init */
+int f16_sm_count(void);
+int f16_set_math_mode(int mode);      /* F16_MATH_*; returns the previous mode */
+int f16_set_clr_mode(int mode);       /* F16_CLR_*; rebuilds the device tables; returns previous mode */
+void f16_set_default_xcg(double xcg); /* for the legacy Nlplant symbol; default 0.25 or $F16_XCG */
+int f16_set_table_staging(int mode);  /* 1 (default): tables staged in shared memory by TMA bulk copy;
+                                         0: read through L1/L2 with ld.global.nc (for A/B measurements) */
+int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256 (default), 384 or 512 */
+/* sha256 (hex, 64 chars + NUL) of the canonical table payload in use */
+int f16_tables_sha256(char *out65);
+
+/* ---- batched entry points, HOST buffers (H2D/D2H inside the call) ------------------------------------ */
+/* xu_soa [17][N] -> xdot_soa [18][N].  fi / xcg: per-aircraft arrays or NULL to use the defaults. */
+int Nlplant_batch(const double *xu_soa, double *xdot_soa, const unsigned char *fi, int fi_default, const double *xcg,
+                  double xcg_default, long long N, int *status);
+/* env.py::_calc_xdot (env.py:65-103) for N aircraft: x_soa [18][N], u_soa [4][N] -> xdot_soa [18][N]. */
+int calc_xdot_batch(const double *x_soa, const double *u_soa, double *xdot_soa, const unsigned char *fi, int fi_default,
+                    const double *xcg, double xcg_default, long long N, int *status);
+/* K fused explicit-Euler steps of env.py::step (env.py:105-130): x_soa [18][N] in/out, u_soa [4][N].
+ * lqr: NULL = open loop.  status [N] (may be NULL), steps_done [N] (may be NULL) = steps taken before freeze. */
+int step_batch(double *x_soa, const double *u_soa, long long N, int K, double dt, const f16_lqr_t *lqr,
+               const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status,
+               int *steps_done);
+/* Finite-difference Jacobians of _calc_xdot (env.py:294-342): A [N][18][18], B [N][18][4], row-major. */
+int linearise_batch(const double *x_soa, const double *u_soa, long long N, double eps, int scheme, double *A, double *B,
+                    const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
+
+/* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
+int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
+                      int fi_default, const double *xcg, double xcg_default, long long N, int *status);
+int calc_xdot_batch_dev(const double *x_soa, long long ld_x, const double *u_soa, long long ld_u, double *xdot_soa,
+                        long long ld_out, const unsigned char *fi, int fi_default, const double *xcg, double xcg_default,
+                        long long N, int *status);
+int step_batch_dev(double *x_soa, long long ld_x, const double *u_soa, long long ld_u, long long N, int K, double dt,
+                   const f16_lqr_t *lqr /* host pointer */, const unsigned char *fi, int fi_default, const double *xcg,
+                   double xcg_default, int *status, int *steps_done);
+int linearise_batch_dev(const double *x_soa, long long ld_x, const double *u_soa, long long ld_u, long long N, double eps,
+                        int scheme, double *A, double *B, const unsigned char *fi, int fi_default, const double *xcg,
+                        double xcg_default, int *status);
+
+/* ---- parity probes (used by the tests; device work, host buffers) ------------------------------------ */
+/* For N query points (alpha_deg, beta_deg, el): coef [44][N] in the order of the reference aggregators
+ * hifi_C, hifi_damping, hifi_C_lef, hifi_damping_lef, hifi_rudder, hifi_ailerons, hifi_other_coeffs
+ * (hifi_F16_AeroData.c:1871-1934) and cells [8][N] = (lo,hi) of ALPHA, BETA1, DH1, DH2 in getHyperCube's
+ * convention (mexndinterp.c:126-137: exact hit -> lo == hi). */
+int f16_hifi_probe(const double *alpha_deg, const double *beta_deg, const double *el, long long N, double *coef,
+                   int *cells, int *status);
+/* lofi coefficients: out [19][N] = damping[9], dmomdcon[4], clcn[2], cxcm[2], cz, Cy(-.02b+.021da+.086dr) */
+int f16_lofi_probe(const double *alpha_deg, const double *beta_deg, const double *el, const double *dail,
+                   const double *drud, long long N, double *out);
+int atmos_batch(const double *alt, const double *vt, long long N, double *coeff_soa /* [3][N] */);
+
+/* ---- device memory / timing helpers so that callers need no CUDA binding of their own ---------------- */
+void *f16_dev_alloc(unsigned long long bytes);
+void f16_dev_free(void *p);
+void *f16_host_alloc_pinned(unsigned long long bytes);
+void f16_host_free_pinned(void *p);
+int f16_memcpy_h2d(void *dst_dev, const void *src_host, unsigned long long bytes);
+int f16_memcpy_d2h(void *dst_host, const void *src_dev, unsigned long long bytes);
+int f16_memset_dev(void *dst_dev, int value, unsigned long long bytes);
+int f16_sync(void);
+void *f16_stream(void);            /* cudaStream_t the kernels run on */
+int f16_timer_start(void);         /* cudaEventRecord on f16_stream() */
+int f16_timer_stop(float *ms);     /* records, synchronises, returns elapsed ms */
+unsigned long long f16_launch_count(void); /* kernels of this library launched since init */
+/* Sustained FP64 FMA rate of this GPU (TFLOP/s, 2 flop per DFMA) from a register-only DFMA kernel run for
+ * about `ms` milliseconds: the measured denominator of the FP64 roofline. */
+int f16_measure_fp64_peak(double ms, double *tflops);
+/* write a buffer larger than L2 so that the next timed launch starts cold */
+int f16_flush_l2(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F16_B200_H */

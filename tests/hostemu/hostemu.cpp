@@ -1,0 +1,82 @@
+// hostemu.cpp -- DEVELOPMENT AID, TESTS ONLY.  Compiles the device arithmetic header (csrc/f16_model.cuh) for the
+// host so that the kernels' logic (cell search, node-interleaved gathers, operation order) can be checked against
+// the oracle on a machine without a GPU.  It is never part of libf16_b200.so and nothing in the package loads it;
+// the product has no CPU path.
+#include <string>
+#include <vector>
+
+#include "../../f16_mpc_oop_py_b200/csrc/f16_model.cuh"
+#include "../../f16_mpc_oop_py_b200/csrc/f16_tables_host.h"
+
+static std::vector<double> g_hifi, g_lofi;
+
+extern "C" {
+__attribute__((visibility("default"))) int emu_init(const char* path, int clr_from_file) {
+  std::vector<double> payload;
+  std::string src, err;
+  if (!f16::load_canonical(path, "", payload, src, err)) return -1;
+  if (!f16::check_grids(payload, err)) return -2;
+  f16::build_hifi_image(payload, clr_from_file != 0, g_hifi);
+  f16::build_lofi_image(g_lofi);
+  return 0;
+}
+
+__attribute__((visibility("default"))) unsigned emu_nlplant(const double* xu_, double* xd_, int fi, double xcg) {
+  double xu[17], xd[18];
+  for (int i = 0; i < 17; i++) xu[i] = xu_[i];
+  unsigned st = fi ? f16::nlplant_eval<1>(g_hifi.data(), xu, xcg, xd) : f16::nlplant_eval<0>(g_lofi.data(), xu, xcg, xd);
+  for (int i = 0; i < 18; i++) xd_[i] = st ? __builtin_nan("") : xd[i];
+  return st;
+}
+
+__attribute__((visibility("default"))) unsigned emu_calc_xdot(const double* x_, const double* u_, double* xd_, int fi, double xcg) {
+  double x[18], u[4], xd[18];
+  for (int i = 0; i < 18; i++) x[i] = x_[i];
+  for (int i = 0; i < 4; i++) u[i] = u_[i];
+  unsigned st = fi ? f16::calc_xdot<1>(g_hifi.data(), x, u, xcg, xd) : f16::calc_xdot<0>(g_lofi.data(), x, u, xcg, xd);
+  for (int i = 0; i < 18; i++) xd_[i] = st ? __builtin_nan("") : xd[i];
+  return st;
+}
+
+__attribute__((visibility("default"))) unsigned emu_step(double* x_, const double* u_, int K, double dt, int fi, double xcg,
+                                                         const f16::LqrLaw* lqr, int* steps_done) {
+  double x[18], u_in[4];
+  for (int i = 0; i < 18; i++) x[i] = x_[i];
+  for (int i = 0; i < 4; i++) u_in[i] = u_[i];
+  unsigned st = 0;
+  int k = 0;
+  for (; k < K; k++) {
+    st = f16::step_bounds(x, u_in);
+    if (st) break;
+    double u[4], xd[18];
+    if (lqr) f16::lqr_action(*lqr, x, u_in, u);
+    else for (int i = 0; i < 4; i++) u[i] = u_in[i];
+    st = fi ? f16::calc_xdot<1>(g_hifi.data(), x, u, xcg, xd) : f16::calc_xdot<0>(g_lofi.data(), x, u, xcg, xd);
+    if (st) break;
+    for (int i = 0; i < 18; i++) x[i] = x[i] + xd[i] * dt;
+  }
+  for (int i = 0; i < 18; i++) x_[i] = x[i];
+  if (steps_done) *steps_done = k;
+  return st;
+}
+
+__attribute__((visibility("default"))) unsigned emu_hifi_probe(double a, double b, double e, double* o, int* cl) {
+  unsigned st = f16::hifi_envelope(a, b, e);
+  if (st) return st;
+  const double* img = g_hifi.data();
+  f16::HifiLoc L = f16::hifi_locate(img, a, b, e);
+  f16::Coef c;
+  f16::hifi_coefs(img, L, c);
+  const double v[44] = {c.Cx, c.Cz, c.Cm, c.Cy, c.Cn, c.Cl, c.Cxq, c.Cyr, c.Cyp, c.Czq, c.Clr, c.Clp, c.Cmq, c.Cnr, c.Cnp,
+                        c.dCx_lef, c.dCz_lef, c.dCm_lef, c.dCy_lef, c.dCn_lef, c.dCl_lef,
+                        c.dCxq_lef, c.dCyr_lef, c.dCyp_lef, c.dCzq_lef, c.dClr_lef, c.dClp_lef, c.dCmq_lef, c.dCnr_lef, c.dCnp_lef,
+                        c.dCy_r30, c.dCn_r30, c.dCl_r30, c.dCy_a20, c.dCy_a20_lef, c.dCn_a20, c.dCn_a20_lef, c.dCl_a20, c.dCl_a20_lef,
+                        c.dCnbeta, c.dClbeta, c.dCm, c.eta_el, c.dCm_ds};
+  for (int i = 0; i < 44; i++) o[i] = v[i];
+  f16::ref_cell(img + F16_IMG_A, L.a, a, cl[0], cl[1]);
+  f16::ref_cell(img + F16_IMG_B, L.b, b, cl[2], cl[3]);
+  f16::ref_cell(img + F16_IMG_D1, L.d1, e, cl[4], cl[5]);
+  f16::ref_cell(img + F16_IMG_D2, L.d2, e, cl[6], cl[7]);
+  return 0;
+}
+}
