@@ -80,6 +80,7 @@ def _load():
     L.f16_host_free_pinned.restype = None
     L.f16_memcpy_h2d.argtypes = [c_vp, c_vp, ctypes.c_ulonglong]
     L.f16_memcpy_d2h.argtypes = [c_vp, c_vp, ctypes.c_ulonglong]
+    L.f16_memcpy_d2d.argtypes = [c_vp, c_vp, ctypes.c_ulonglong]
     L.f16_memset_dev.argtypes = [c_vp, ctypes.c_int, ctypes.c_ulonglong]
     L.f16_stream.restype = c_vp
     L.f16_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_float)]

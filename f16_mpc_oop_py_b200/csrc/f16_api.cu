@@ -373,8 +373,9 @@ int linearise_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
     set_err("linearise_batch_dev: bad argument");
     return F16_ERR_ARG;
   }
-  CK(DISPATCH(launch_linearise, cfg(true), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, N,
-              eps, scheme, A, B, status));
+  // always the strict build: the difference quotient multiplies rounding noise by 1/eps (1e5)
+  CK(f16::strict::launch_linearise(cfg(true), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u,
+                                   N, eps, scheme, A, B, status));
   return F16_OK;
 }
 
@@ -482,8 +483,10 @@ int linearise_batch(const double* x_soa, const double* u_soa, long long N, doubl
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, x_soa, 18 * n * 8);
   H2D(G.b_in2.p, u_soa, 4 * n * 8);
-  CK(DISPATCH(launch_linearise, cfg(true), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p,
-              N, (const double*)G.b_in2.p, N, N, eps, scheme, (double*)G.b_a.p, (double*)G.b_b.p, (int*)G.b_st.p));
+  // always the strict build: the difference quotient multiplies rounding noise by 1/eps (1e5)
+  CK(f16::strict::launch_linearise(cfg(true), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
+                                   (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, eps, scheme,
+                                   (double*)G.b_a.p, (double*)G.b_b.p, (int*)G.b_st.p));
   D2H(A, G.b_a.p, 324 * n * 8);
   D2H(B, G.b_b.p, 72 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);
@@ -591,6 +594,13 @@ int f16_memcpy_d2h(void* dst_host, const void* src_dev, unsigned long long bytes
   if (rc != F16_OK) return rc;
   CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, G.stream));
   CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+int f16_memcpy_d2d(void* dst_dev, const void* src_dev, unsigned long long bytes) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  CK(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, G.stream));
   return F16_OK;
 }
 int f16_memset_dev(void* dst_dev, int value, unsigned long long bytes) {

@@ -441,8 +441,11 @@ static StepKern pick_step(bool smem_tables, int& threads) {
   if (!smem_tables) { threads = 256; return step_kernel<FI, false, LQR, 256>; }
   if (threads <= 256) { threads = 256; return step_kernel<FI, true, LQR, 256>; }
   if (threads <= 384) { threads = 384; return step_kernel<FI, true, LQR, 384>; }
-  threads = 512;
-  return step_kernel<FI, true, LQR, 512>;
+  if (threads <= 512) { threads = 512; return step_kernel<FI, true, LQR, 512>; }
+  if (threads <= 640) { threads = 640; return step_kernel<FI, true, LQR, 640>; }
+  if (threads <= 768) { threads = 768; return step_kernel<FI, true, LQR, 768>; }
+  threads = 1024;
+  return step_kernel<FI, true, LQR, 1024>;
 }
 
 cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x,

@@ -116,7 +116,8 @@ int calc_xdot_batch(const double *x_soa, const double *u_soa, double *xdot_soa, 
 int step_batch(double *x_soa, const double *u_soa, long long N, int K, double dt, const f16_lqr_t *lqr,
                const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status,
                int *steps_done);
-/* Finite-difference Jacobians of _calc_xdot (env.py:294-342): A [N][18][18], B [N][18][4], row-major. */
+/* Finite-difference Jacobians of _calc_xdot (env.py:294-342): A [N][18][18], B [N][18][4], row-major.
+ * Always computed by the strict (no FMA contraction) build: the quotient amplifies rounding noise by 1/eps. */
 int linearise_batch(const double *x_soa, const double *u_soa, long long N, double eps, int scheme, double *A, double *B,
                     const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
 
@@ -152,6 +153,7 @@ void *f16_host_alloc_pinned(unsigned long long bytes);
 void f16_host_free_pinned(void *p);
 int f16_memcpy_h2d(void *dst_dev, const void *src_host, unsigned long long bytes);
 int f16_memcpy_d2h(void *dst_host, const void *src_dev, unsigned long long bytes);
+int f16_memcpy_d2d(void *dst_dev, const void *src_dev, unsigned long long bytes); /* asynchronous on f16_stream() */
 int f16_memset_dev(void *dst_dev, int value, unsigned long long bytes);
 int f16_sync(void);
 void *f16_stream(void);            /* cudaStream_t the kernels run on */
