@@ -349,14 +349,14 @@ def test_step_table_staging_variants_agree(f16):
     g = load_golden("xcg35")
     x, u = perturbed_trim(20_000, g["x_trim"], seed=6)
     outs = []
-    for staging, threads in ((1, 256), (1, 384), (1, 512), (0, 256)):
+    for staging, threads in ((1, 256), (1, 384), (1, 512), (1, 640), (1, 768), (1, 1024), (0, 256)):
         f16.lib.f16_set_table_staging(staging)
         f16.lib.f16_set_step_threads(threads)
         fb = f16.F16Batch(x, u, xcg=0.35)
         fb.step(K=50)
         outs.append(fb.x.copy())
     f16.lib.f16_set_table_staging(1)
-    f16.lib.f16_set_step_threads(256)
+    f16.lib.f16_set_step_threads(512)
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])
 
