@@ -183,7 +183,8 @@ def run_ours(args):
     tag = "xcg35" if args.workload == "lqr" else "xcg25"
     xcg = 0.35 if args.workload == "lqr" else 0.25
     x_trim, u_trim, mpc_idx = trim_state(tag)
-    x, u = perturbed_trim(n, x_trim, u_trim, seed=0xF16 + rank)
+    from f16_mpc_oop_py_b200.shard import rank_seed
+    x, u = perturbed_trim(n, x_trim, u_trim, seed=rank_seed(0xF16, rank))
     law = None
     if args.workload == "lqr":
         K = np.zeros((3, 9))
@@ -271,16 +272,12 @@ def run_ours(args):
     for p in (hx, hu, hs):
         L.f16_host_free_pinned(p)
 
-    # max over ranks, survivors over ranks
-    if dist:
-        import torch
-        t = torch.tensor([elapsed_ms, kernel_ms, e2e_t], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, kernel_ms, e2e_t = (float(v) for v in t.tolist())
-        stats = torch.tensor([alive], dtype=torch.float64, device="cuda")
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)      # the only collective: end-of-run statistics
-        alive = float(torch.stack(gathered).mean())
+    # max over ranks (timings are the slowest rank's); the only collective: end-of-run statistics
+    from f16_mpc_oop_py_b200 import shard
+    dev = f"cuda:{local}" if dist else "cpu"
+    elapsed_ms, kernel_ms, e2e_t = shard.max_over_ranks(dist, [elapsed_ms, kernel_ms, e2e_t], dev)
+    summary = shard.gather_summaries(dist, shard.summarise(xf, st), dev)
+    alive = summary["alive_fraction"]
 
     total_steps = float(world) * n * ke * args.steps
     value = total_steps / (elapsed_ms * 1e-3)

@@ -5,6 +5,7 @@ env.py Euler step and the finite-difference linearise, as hand-written sm_100a C
 this package loads that library and fails if it has not been built; there is no CPU fallback.
 """
 from . import parameters
+from . import shard
 from ._lib import (CLR_AS_BUILT, CLR_FROM_FILE, FD_CENTRAL, FD_FORWARD, MATH_FAST, MATH_STRICT, F16Error, LqrLaw, init,
                    lib)
 from .plant import F16Batch, atmos, make_lqr, nlplant
