@@ -48,6 +48,7 @@ struct State {
   std::string table_source;
   double* d_hifi = nullptr;
   double* d_lofi = nullptr;
+  double* d_hifi_fast = nullptr;
   int math_mode = F16_MATH_STRICT;
   int clr_mode = F16_CLR_AS_BUILT;
   bool smem_tables = true;
@@ -99,6 +100,9 @@ int upload_tables() {
   f16::build_hifi_image(G.payload, G.clr_mode == F16_CLR_FROM_FILE, img);
   if (!G.d_hifi) CK(cudaMalloc(&G.d_hifi, F16_IMG_HIFI_BYTES));
   CK(cudaMemcpy(G.d_hifi, img.data(), F16_IMG_HIFI_BYTES, cudaMemcpyHostToDevice));
+  f16::build_hifi_fast_image(G.payload, G.clr_mode == F16_CLR_FROM_FILE, img);
+  if (!G.d_hifi_fast) CK(cudaMalloc(&G.d_hifi_fast, F16_FI_BYTES));
+  CK(cudaMemcpy(G.d_hifi_fast, img.data(), F16_FI_BYTES, cudaMemcpyHostToDevice));
   f16::build_lofi_image(img);
   if (!G.d_lofi) CK(cudaMalloc(&G.d_lofi, F16_IMG_LOFI_BYTES));
   CK(cudaMemcpy(G.d_lofi, img.data(), F16_IMG_LOFI_BYTES, cudaMemcpyHostToDevice));
@@ -168,7 +172,7 @@ f16::LaunchCfg cfg(bool smem_tables) {
   c.launch_counter = &G.launches;
   return c;
 }
-f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi}; }
+f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi, G.d_hifi_fast}; }
 f16::BatchSel sel_of(const unsigned char* fi, int fi_default, const double* xcg, double xcg_default) {
   return f16::BatchSel{fi, fi_default, xcg, xcg_default};
 }
@@ -210,6 +214,7 @@ void f16_shutdown(void) {
   for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush}) b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
+  if (G.d_hifi_fast) cudaFree(G.d_hifi_fast);
   if (G.pin) cudaFreeHost(G.pin);
   cudaEventDestroy(G.ev0);
   cudaEventDestroy(G.ev1);

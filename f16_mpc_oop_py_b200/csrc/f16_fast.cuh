@@ -1,0 +1,335 @@
+// f16_fast.cuh -- the throughput arithmetic of the fused hifi Euler step (F16_MATH_FAST).
+//
+// Same model as f16_model.cuh (which keeps the reference's operation order and is the parity build), re-associated
+// for the B200 FP64 pipe.  Every substitution below moves a derivative by a few ulp of its natural scale; the
+// budget (tests/test_gpu_parity.py, tests/test_model_host.py) is 1e-12 scaled per derivative and 1e-9 after 10 s.
+//
+//   * tables: the "fast image" stores, per alpha CELL, the value at the lower node and the difference to the upper
+//     node, so an alpha interpolation is ONE fma(lambda, d, f) instead of lambda*f2 + (1-lambda)*f1
+//     (mexndinterp.c:196-197), and one LDS.128 fetches (f, d);
+//   * the rudder / aileron / lef tables of one force or moment are combined with their weights at each beta node
+//     before the beta interpolation (hifi_F16_AeroData.c:1892-1926 + nlplant.c:333-377 are linear in the tables);
+//   * sin/cos: alpha and beta are inside [-pi/4, pi/4] whenever the hifi envelope check passed, so they need no
+//     argument reduction; phi, theta, psi use a two-constant Cody-Waite reduction; coefficients live in the
+//     constant bank (no UMOV pairs in the instruction stream);
+//   * rho = rho0 * tfac^4.14 (nlplant.c:478): tfac in [0.297, 1] on the bounded altitude range, evaluated as
+//     c^4.14 * (1+s)^4.14 with c from a 48-entry table and a degree-9 binomial series in |s| <= 0.027;
+//   * Vt/alpha/beta dots use U = vt ca cb, V = vt sb, W = vt sa cb to cancel vt analytically; qbar/ps of the LEF
+//     schedule (utils.py:296) cancels rho.
+//
+// Reference lines are cited next to each block; names follow C/nlplant.c.
+#pragma once
+#include "f16_model.cuh"
+
+#if defined(__CUDACC__)
+#define F16_FD __device__ __forceinline__
+#define F16_KCONST __constant__
+#else
+#define F16_FD static inline __attribute__((always_inline))
+#define F16_KCONST static const
+#endif
+
+namespace f16 {
+namespace fastmath {
+
+// Constant-bank operands.  sin/cos kernels on [-pi/4, pi/4]: the classic fdlibm minimax coefficients.
+struct K_t {
+  double S[6], C[6];
+  double two_over_pi, pio2_hi, pio2_mid;
+  double PW[9];  // binomial coefficients C(4.14, k), k = 1..9
+};
+F16_KCONST K_t K = {
+    {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+     -2.50507602534068634195e-08, 1.58969099521155010221e-10},
+    {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,
+     2.08757232129817482790e-09, -1.13596475577881948265e-11},
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17,
+    {4.14, 6.499799999999999, 4.636523999999999, 1.321409339999999, 0.036999461519999895, -0.005303256151199987,
+     0.0014091509201759967, -0.0005037714539629189, 0.00021606197914409635}};
+
+F16_FD int lo32(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(v);
+#else
+  long long b;
+  __builtin_memcpy(&b, &v, 8);
+  return (int)(b & 0xffffffffLL);
+#endif
+}
+F16_FD double flip_sign(double v, int mask_hi) {  // mask_hi = 0 or 0x80000000
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ mask_hi, __double2loint(v));
+#else
+  unsigned long long b;
+  __builtin_memcpy(&b, &v, 8);
+  b ^= ((unsigned long long)(unsigned)mask_hi) << 32;
+  __builtin_memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+// sin and cos for |x| <= pi/4 (16 FP64 instructions)
+F16_FD void sincos_quarter(double x, double& s, double& c) {
+  const double z = x * x;
+  double ps = fma(z, K.S[5], K.S[4]);
+  double pc = fma(z, K.C[5], K.C[4]);
+  ps = fma(z, ps, K.S[3]);
+  pc = fma(z, pc, K.C[3]);
+  ps = fma(z, ps, K.S[2]);
+  pc = fma(z, pc, K.C[2]);
+  ps = fma(z, ps, K.S[1]);
+  pc = fma(z, pc, K.C[1]);
+  ps = fma(z, ps, K.S[0]);
+  pc = fma(z, pc, K.C[0]);
+  s = fma(x * z, ps, x);
+  c = fma(z, fma(z, pc, -0.5), 1.0);
+}
+
+#if defined(__CUDACC__)
+__device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
+#else
+static void sincos_slow(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+#endif
+
+// sin and cos of any argument: j = rint(x 2/pi), r = x - j pi/2 in two FMAs, quadrant fix-up on the sign bits.
+// |x| > 1e5 (never reached by a bounded flight state) takes libm's path.
+F16_FD void sincos_any(double x, double& s, double& c) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, K.two_over_pi, magic);
+  const double j = t - magic;
+  const int q = lo32(t);
+  double r = fma(-j, K.pio2_hi, x);
+  r = fma(-j, K.pio2_mid, r);
+  if (fabs(x) > 1.0e5) {
+    sincos_slow(x, &s, &c);
+    return;
+  }
+  double ss, cc;
+  sincos_quarter(r, ss, cc);
+  const bool sw = (q & 1) != 0;
+  const double s0 = sw ? cc : ss, c0 = sw ? ss : cc;
+  s = flip_sign(s0, (q & 2) << 30);
+  c = flip_sign(c0, ((q + 1) & 2) << 30);
+}
+
+// 0.5 * rho0 * tfac^4.14 for tfac in [0.28125, 1.03125): table of centres + binomial series (15 FP64 instructions)
+F16_FD double half_rho(const double* img, double tfac) {
+  const double magic = 6755399441055744.0;
+  const double u = fma(tfac, 64.0, -18.5);
+  const double tm = u + magic;
+  int i = lo32(tm);
+  const double d = u - (tm - magic);  // |d| <= 0.5, exact
+  i = i < 0 ? 0 : (i > F16_FI_NPOW - 1 ? F16_FI_NPOW - 1 : i);
+  const d2 e = ld2(img + F16_FI_POW + 2 * i);
+  const double s = d * e.x;  // (tfac - c_i) / c_i
+  double p = fma(s, K.PW[8], K.PW[7]);
+  p = fma(s, p, K.PW[6]);
+  p = fma(s, p, K.PW[5]);
+  p = fma(s, p, K.PW[4]);
+  p = fma(s, p, K.PW[3]);
+  p = fma(s, p, K.PW[2]);
+  p = fma(s, p, K.PW[1]);
+  p = fma(s, p, K.PW[0]);
+  p = fma(s, p, 1.0);
+  return p * e.y;
+}
+
+F16_FD double rcp(double v) { return 1.0 / v; }
+
+// value of table `slot` of an (f, d) node at alpha weight la
+F16_FD double fd(const double* node, int slot, double la) {
+  const d2 v = ld2(node + 2 * slot);
+  return fma(la, v.y, v.x);
+}
+F16_FD double mix(double lam, double lo, double hi) { return fma(lam, hi - lo, lo); }
+
+// cheap "any violation" form of env.py:117 + the NaN rule of step_bounds(): true when every bounded state is
+// inside its closed interval (a NaN fails the comparison) and no unbounded state is NaN
+F16_FD bool step_ok(const double (&x)[18]) {
+  bool ok = (x[2] >= 0.0) && (x[2] <= 100000.0);
+  ok = ok && (x[6] >= 0.0) && (x[6] <= 900.0);
+  ok = ok && (x[7] >= -20.0) && (x[7] <= 90.0);
+  ok = ok && (fabs(x[8]) <= 30.0) && (fabs(x[9]) <= 300.0) && (fabs(x[10]) <= 100.0) && (fabs(x[11]) <= 50.0);
+  ok = ok && (x[12] >= 1000.0) && (x[12] <= 19000.0);
+  ok = ok && (fabs(x[13]) <= 25.0) && (fabs(x[14]) <= 21.5) && (fabs(x[15]) <= 30.0);
+  ok = ok && (x[16] >= 0.0) && (x[16] <= 25.0);
+  ok = ok && !either_nan(x[0], x[1]) && !either_nan(x[3], x[4]) && !either_nan(x[5], x[17]);
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// env.py::_calc_xdot (env.py:65-103) for the hifi model, all 18 derivatives.  `img` is the fast image.
+// Precondition (checked by the caller through step_ok): states inside parameters.py bounds, no NaN.
+// Returns false when alpha / beta leave the hifi tables (the caller then reports the exact status word).
+// ------------------------------------------------------------------------------------------------------
+F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&u)[4], double xcg, double (&xd)[18]) {
+  const double g = 32.17, m = 636.94, B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
+  const double r2d = 180.0 / 3.141592653589793;
+  const double Jy = 55814.0, Jxz = 982.0, Jz = 63100.0, Jx = 9496.0;
+
+  const double alpha = x[7] * r2d, beta = x[8] * r2d, el = x[13];
+  // hifi_envelope(): elevator range is already guaranteed by the |x[13]| <= 25 bound
+  if (!((alpha >= -20.0) && (alpha <= 45.0) && (fabs(beta) <= 30.0))) return false;
+
+  const AxisLoc La = locate_alpha(img, alpha), Lb = locate_beta(img, beta), L1 = locate_dh1(img, el),
+                L2 = locate_dh2(img, el);
+  const double la = La.lam, lb = Lb.lam, l1 = L1.lam, l2 = L2.lam;
+
+  double sa, ca, sb, cb, st, ct, sphi, cphi, spsi, cpsi;
+  sincos_quarter(x[7], sa, ca);
+  sincos_quarter(x[8], sb, cb);
+  sincos_any(x[4], st, ct);
+  sincos_any(x[3], sphi, cphi);
+  sincos_any(x[5], spsi, cpsi);
+
+  double vt = x[6];
+  if (vt <= 0.01) vt = 0.01;  // nlplant.c:104
+  const double P = x[9], Q = x[10], R = x[11], T = x[12];
+
+  // atmos, nlplant.c:467-490: only qbar (Nlplant) and qbar/ps (upd_lef, utils.py:291-296) are consumed here
+  const double tfac = fma(-.703e-5, x[2], 1.0);
+  const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
+  const double hrho = half_rho(img, tfac);
+  const double qbar = hrho * (vt * vt);
+  const double inv_temp = rcp(temp), inv_vt = rcp(vt), inv_ct = rcp(ct), inv_cb = rcp(cb);
+
+  const double dail = x[14] * (1.0 / 21.5), drud = x[15] * (1.0 / 30.0);  // nlplant.c:123-124
+  const double dlef = fma(x[16], -(1.0 / 25.0), 1.0);                      // nlplant.c:125
+
+  // navigation + kinematics, nlplant.c:148-176
+  const double U = vt * ca * cb, V = vt * sb, W = vt * sa * cb;
+  xd[0] = U * (ct * cpsi) + V * (sphi * cpsi * st - cphi * spsi) + W * (cphi * st * cpsi + sphi * spsi);
+  xd[1] = U * (ct * spsi) + V * (sphi * spsi * st + cphi * cpsi) + W * (cphi * st * spsi - sphi * cpsi);
+  xd[2] = U * st - V * (sphi * ct) - W * (cphi * ct);
+  const double qr = Q * sphi + R * cphi;
+  xd[3] = fma(st * inv_ct, qr, P);
+  xd[4] = Q * cphi - R * sphi;
+  xd[5] = qr * inv_ct;
+
+  // weights of the damping terms, nlplant.c:333-377
+  const double qQ = (0.5 * cbar) * inv_vt * Q, bR = (0.5 * B) * inv_vt * R, bP = (0.5 * B) * inv_vt * P;
+
+  double Cx_tot, Cz_tot, Cm_tot, Cy_tot, Cn_tot, Cl_tot;
+  double dCz_lef, Czq_dyn;
+
+  // ---- alpha x beta group (hifi_C_lef, hifi_rudder, hifi_ailerons: hifi:1892-1926) ----
+  {
+    // weights of the five tables of a lateral coefficient:  C + dC_lef dlef + (dC_a20 + dC_a20_lef dlef) dail + dC_r30 drud
+    const double w_a = dail * dlef;            // C_a20_lef
+    const double w_a20 = dail - w_a;           // C_a20
+    const double w_lef = dlef - w_a;           // C_lef
+    const double w_0 = -(w_lef + w_a20 + w_a + drud);  // the dele = 0 slice subtracted by every delta
+    const double* n0 = img + F16_FI_G2 + (Lb.lo * F16_FI_NAC + La.lo) * F16_FI_G2_STRIDE;
+    const double* n1 = n0 + F16_FI_NAC * F16_FI_G2_STRIDE;
+    double dx[2], dz[2], dm[2], y[2], n[2], l[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 2; k++) {
+      const double* p = k ? n1 : n0;
+      dx[k] = fd(p, FG2_Cx_lef, la) - fd(p, FG2_Cx0, la);
+      dz[k] = fd(p, FG2_Cz_lef, la) - fd(p, FG2_Cz0, la);
+      dm[k] = fd(p, FG2_Cm_lef, la) - fd(p, FG2_Cm0, la);
+      double a = fd(p, FG2_Cy, la) * (1.0 + w_0);
+      a = fma(fd(p, FG2_Cy_lef, la), w_lef, a);
+      a = fma(fd(p, FG2_Cy_a20, la), w_a20, a);
+      a = fma(fd(p, FG2_Cy_a20_lef, la), w_a, a);
+      y[k] = fma(fd(p, FG2_Cy_r30, la), drud, a);
+      a = fd(p, FG2_Cn0, la) * w_0;
+      a = fma(fd(p, FG2_Cn_lef, la), w_lef, a);
+      a = fma(fd(p, FG2_Cn_a20, la), w_a20, a);
+      a = fma(fd(p, FG2_Cn_a20_lef, la), w_a, a);
+      n[k] = fma(fd(p, FG2_Cn_r30, la), drud, a);
+      a = fd(p, FG2_Cl0, la) * w_0;
+      a = fma(fd(p, FG2_Cl_lef, la), w_lef, a);
+      a = fma(fd(p, FG2_Cl_a20, la), w_a20, a);
+      a = fma(fd(p, FG2_Cl_a20_lef, la), w_a, a);
+      l[k] = fma(fd(p, FG2_Cl_r30, la), drud, a);
+    }
+    dCz_lef = mix(lb, dz[0], dz[1]);
+    Cx_tot = mix(lb, dx[0], dx[1]) * dlef;
+    Cm_tot = mix(lb, dm[0], dm[1]) * dlef;
+    Cy_tot = mix(lb, y[0], y[1]);
+    Cn_tot = mix(lb, n[0], n[1]);
+    Cl_tot = mix(lb, l[0], l[1]);
+  }
+  // ---- alpha x beta x DH2: Cn, Cl (hifi:1876-1877) ----
+  {
+    const double* p = img + F16_FI_G3B + ((L2.lo * F16_N_B + Lb.lo) * F16_FI_NAC + La.lo) * F16_FI_G3B_STRIDE;
+    const int sb_ = F16_FI_NAC * F16_FI_G3B_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3B_STRIDE;
+    const double n_lo = mix(lb, fd(p, 0, la), fd(p + sb_, 0, la)), n_hi = mix(lb, fd(p + sd, 0, la), fd(p + sd + sb_, 0, la));
+    const double l_lo = mix(lb, fd(p, 1, la), fd(p + sb_, 1, la)), l_hi = mix(lb, fd(p + sd, 1, la), fd(p + sd + sb_, 1, la));
+    Cn_tot += mix(l2, n_lo, n_hi);
+    Cl_tot += mix(l2, l_lo, l_hi);
+  }
+  // ---- alpha x beta x DH1: Cx, Cz, Cm (hifi:1872-1874) and eta_el (hifi:1932) ----
+  double Cm3;
+  {
+    const double* p = img + F16_FI_G3A + ((L1.lo * F16_N_B + Lb.lo) * F16_FI_NAC + La.lo) * F16_FI_G3A_STRIDE;
+    const int sb_ = F16_FI_NAC * F16_FI_G3A_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3A_STRIDE;
+    const double x_lo = mix(lb, fd(p, 0, la), fd(p + sb_, 0, la)), x_hi = mix(lb, fd(p + sd, 0, la), fd(p + sd + sb_, 0, la));
+    const double z_lo = mix(lb, fd(p, 1, la), fd(p + sb_, 1, la)), z_hi = mix(lb, fd(p + sd, 1, la), fd(p + sd + sb_, 1, la));
+    const double m_lo = mix(lb, fd(p, 2, la), fd(p + sb_, 2, la)), m_hi = mix(lb, fd(p + sd, 2, la), fd(p + sd + sb_, 2, la));
+    Cx_tot += mix(l1, x_lo, x_hi);
+    Cz_tot = fma(dCz_lef, dlef, mix(l1, z_lo, z_hi));
+    Cm3 = mix(l1, m_lo, m_hi);
+    const d2 e = ld2(img + F16_FI_ETA + 2 * L1.lo);
+    Cm3 *= fma(l1, e.y, e.x);
+  }
+  // ---- alpha-only group: damping, lef damping, other (hifi:1880-1890,1901-1911,1928-1934) ----
+  {
+    const double* p = img + F16_FI_G1 + La.lo * F16_FI_G1_STRIDE;
+    Cx_tot = fma(qQ, fma(fd(p, FG1_dCxq_lef, la), dlef, fd(p, FG1_Cxq, la)), Cx_tot);
+    // nlplant.c:339 uses delta_Cz_lef where delta_Czq_lef was meant -- reproduced
+    Czq_dyn = fma(dCz_lef, dlef, fd(p, FG1_Czq, la));
+    Cz_tot = fma(qQ, Czq_dyn, Cz_tot);
+    Cm_tot += Cm3 + fd(p, FG1_dCm, la);
+    Cm_tot = fma(qQ, fma(fd(p, FG1_dCmq_lef, la), dlef, fd(p, FG1_Cmq, la)), Cm_tot);
+    Cm_tot = fma(Cz_tot, xcgr - xcg, Cm_tot);
+    Cy_tot = fma(bR, fma(fd(p, FG1_dCyr_lef, la), dlef, fd(p, FG1_Cyr, la)), Cy_tot);
+    Cy_tot = fma(bP, fma(fd(p, FG1_dCyp_lef, la), dlef, fd(p, FG1_Cyp, la)), Cy_tot);
+    Cn_tot = fma(bR, fma(fd(p, FG1_dCnr_lef, la), dlef, fd(p, FG1_Cnr, la)), Cn_tot);
+    Cn_tot = fma(bP, fma(fd(p, FG1_dCnp_lef, la), dlef, fd(p, FG1_Cnp, la)), Cn_tot);
+    Cn_tot = fma(fd(p, FG1_dCnbeta, la), beta, Cn_tot);
+    Cn_tot = fma(Cy_tot, -(xcgr - xcg) * (cbar / B), Cn_tot);
+    Cl_tot = fma(bR, fma(fd(p, FG1_dClr_lef, la), dlef, fd(p, FG1_Clr, la)), Cl_tot);
+    Cl_tot = fma(bP, fma(fd(p, FG1_dClp_lef, la), dlef, fd(p, FG1_Clp, la)), Cl_tot);
+    Cl_tot = fma(fd(p, FG1_dClbeta, la), beta, Cl_tot);
+  }
+
+  // body-axis accelerations, nlplant.c:383-387
+  const double qS_m = qbar * (S / m);
+  const double Udot = R * V - Q * W - g * st + qS_m * Cx_tot + T * (1.0 / m);
+  const double Vdot = P * W - R * U + g * ct * sphi + qS_m * Cy_tot;
+  const double Wdot = Q * U - P * V + g * ct * cphi + qS_m * Cz_tot;
+  // nlplant.c:393-405 with U = vt ca cb, V = vt sb, W = vt sa cb substituted (vt cancels)
+  const double vtd = ca * cb * Udot + sb * Vdot + sa * cb * Wdot;
+  xd[6] = vtd;
+  xd[7] = (ca * Wdot - sa * Udot) * (inv_vt * inv_cb);
+  xd[8] = (Vdot - sb * vtd) * (inv_vt * inv_cb);
+
+  // moments, nlplant.c:413-436 (Heng = 0)
+  const double qSb = qbar * (S * B);
+  const double L_tot = Cl_tot * qSb, N_tot = Cn_tot * qSb, M_tot = Cm_tot * (qbar * (S * cbar));
+  const double denom = Jx * Jz - Jxz * Jxz;
+  xd[9] = (Jz * L_tot + Jxz * N_tot - (Jz * (Jz - Jy) + Jxz * Jxz) * (Q * R) + (Jxz * (Jx - Jy + Jz)) * (P * Q)) * (1.0 / denom);
+  xd[10] = (M_tot + (Jz - Jx) * (P * R) - Jxz * (P * P - R * R)) * (1.0 / Jy);
+  xd[11] = (Jx * N_tot + Jxz * L_tot + (Jx * (Jx - Jy) + Jxz * Jxz) * (P * Q) - (Jxz * (Jx - Jy + Jz)) * (Q * R)) * (1.0 / denom);
+
+  // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)
+  const double atmos_out = (x[6] * x[6]) * inv_temp * (0.5 * 9.05 / 1715.0);
+  const double alpha_deg = (x[7] * 180.0) * (1.0 / 3.141592653589793);
+  const double lf_in = fma(2.0, alpha_deg, x[17]);
+  double lef_cmd = fma(lf_in, 1.38, 1.45) - atmos_out;
+  lef_cmd = clipd(lef_cmd, 0, 25);
+  xd[12] = clipd(clipd(u[0], 1000, 19000) - x[12], -10000, 10000);
+  xd[13] = clipd(20.2 * (clipd(u[1], -25, 25) - x[13]), -60, 60);
+  xd[14] = clipd(20.2 * (clipd(u[2], -21.5, 21.5) - x[14]), -80, 80);
+  xd[15] = clipd(20.2 * (clipd(u[3], -30, 30) - x[15]), -120, 120);
+  xd[16] = clipd((1 / 0.136) * (lef_cmd - x[16]), -25, 25);
+  xd[17] = (alpha_deg - lf_in) * 7.25;
+  return true;
+}
+
+}  // namespace fastmath
+}  // namespace f16

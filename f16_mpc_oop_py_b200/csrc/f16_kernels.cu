@@ -10,6 +10,9 @@
 #include <stdint.h>
 
 #include "f16_kernels.cuh"
+#if defined(F16_FAST)
+#include "f16_fast.cuh"
+#endif
 
 #ifndef F16_NS
 #error "compile with -DF16_NS=strict or -DF16_NS=fast"
@@ -193,6 +196,69 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
     if (steps_done) steps_done[n] = k;
   }
 }
+
+#if defined(F16_FAST)
+// ------------------------------------------------------------------------------------------------------
+// step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
+// (fast table image: 171 KB in shared memory, one CTA per SM).  The per-step checks are the cheap "all inside"
+// form; the exact status word is rebuilt from the frozen state when an aircraft stops.
+// ------------------------------------------------------------------------------------------------------
+constexpr int FAST_SMEM_BYTES = F16_FI_BYTES + 16;
+
+template <bool SMEM, bool LQR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
+                      const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
+                      int* __restrict__ status, int* __restrict__ steps_done) {
+  const double* img = tabs.hifi_fast;
+  if (SMEM) {
+    stage_tables_tma<F16_FI_BYTES>(f16_smem, img, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
+    img = reinterpret_cast<const double*>(f16_smem);
+  }
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<1>(sel, n);
+    if (own == 0) continue;
+    if (own < 0) {
+      if (status) status[n] = (int)ST_FIDELITY;
+      if (steps_done) steps_done[n] = 0;
+      continue;
+    }
+    double x[18], u_in[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
+    const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+    const bool u_ok = !(either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3]));
+    int k = 0;
+    if (u_ok) {
+#pragma unroll 1
+      for (; k < K; k++) {
+        if (!fastmath::step_ok(x)) break;  // env.py:117 -- the reference exit()s here; we freeze this aircraft
+        double u[4], xd[18];
+        if (LQR) {
+          lqr_action(c_lqr, x, u_in, u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) u[i] = u_in[i];
+        }
+        if (!fastmath::calc_xdot_hifi(img, x, u, xcg, xd)) break;
+#pragma unroll
+        for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);  // env.py:126
+      }
+    }
+    unsigned st = 0;
+    if (k < K) {  // stopped early: the exact status word of the frozen state
+      st = step_bounds(x, u_in);
+      if (!st) st = hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (status) status[n] = (int)st;
+    if (steps_done) steps_done[n] = k;
+  }
+}
+#endif  // F16_FAST
 
 // ------------------------------------------------------------------------------------------------------
 // linearise_batch: finite-difference A [18x18], B [18x4] of _calc_xdot (env.py:294-342).
@@ -436,6 +502,19 @@ cudaError_t launch_calc_xdot(const LaunchCfg& cfg, const DevTables& tabs, const 
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*);
 
+#if defined(F16_FAST)
+template <bool LQR>
+static StepKern pick_step_hifi_fast(bool smem_tables, int& threads) {
+  if (!smem_tables) { threads = 256; return step_hifi_fast_kernel<false, LQR, 256>; }
+  if (threads <= 256) { threads = 256; return step_hifi_fast_kernel<true, LQR, 256>; }
+  if (threads <= 384) { threads = 384; return step_hifi_fast_kernel<true, LQR, 384>; }
+  if (threads <= 512) { threads = 512; return step_hifi_fast_kernel<true, LQR, 512>; }
+  if (threads <= 640) { threads = 640; return step_hifi_fast_kernel<true, LQR, 640>; }
+  threads = 768;
+  return step_hifi_fast_kernel<true, LQR, 768>;
+}
+#endif
+
 template <int FI, bool LQR>
 static StepKern pick_step(bool smem_tables, int& threads) {
   if (!smem_tables) { threads = 256; return step_kernel<FI, false, LQR, 256>; }
@@ -460,9 +539,15 @@ cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const Batch
   for (int FI = 1; FI >= 0 && e == cudaSuccess; FI--) {
     if (!wants(sel, FI)) continue;
     int threads = cfg.step_threads;
+#if defined(F16_FAST)
+    StepKern k = FI ? (lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads))
+                    : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
+    const int smem = FI ? (cfg.smem_tables ? FAST_SMEM_BYTES : 0) : table_smem<0>(cfg.smem_tables);
+#else
     StepKern k = FI ? (lqr_host ? pick_step<1, true>(cfg.smem_tables, threads) : pick_step<1, false>(cfg.smem_tables, threads))
                     : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
     const int smem = FI ? table_smem<1>(cfg.smem_tables) : table_smem<0>(cfg.smem_tables);
+#endif
     e = launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
   }
   return e;

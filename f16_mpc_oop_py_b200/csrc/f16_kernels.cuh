@@ -10,6 +10,7 @@ namespace f16 {
 struct DevTables {
   const double* hifi;  // F16_IMG_HIFI_DOUBLES, 16-byte aligned
   const double* lofi;  // F16_IMG_LOFI_DOUBLES
+  const double* hifi_fast;  // F16_FI_DOUBLES: the (f, d) image of f16_fast.cuh, used by the F16_MATH_FAST step kernel
 };
 
 struct BatchSel {           // which aircraft run which model

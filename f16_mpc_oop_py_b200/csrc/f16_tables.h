@@ -78,6 +78,39 @@ enum F16G2Slot {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// device image, hifi, "fast" layout (f16_fast.cuh): per alpha CELL the value at the lower node f and the difference
+// d to the upper node, interleaved (f, d), so one LDS.128 + one FMA is an alpha interpolation.
+// ---------------------------------------------------------------------------------------------------
+// the first 48 doubles (breakpoints) equal the strict image so hifi_locate() serves both
+#define F16_FI_NAC 13        // alpha cells (-20:5:45)
+#define F16_FI_ETA 48        // eta_el per DH1 cell: (f, d) x 4
+#define F16_FI_POW 56        // 48 x (1/(64 c_i), 0.5*rho0*c_i^4.14), c_i = (18.5 + i)/64
+#define F16_FI_NPOW 48
+#define F16_FI_G1 152        // alpha-only group: 13 cells x 20 tables x (f, d)
+#define F16_FI_G1_STRIDE 40
+#define F16_FI_G3B 672       // (Cn, Cl) on DH2 x beta x alpha-cell: 3*19*13 nodes x 2 x (f, d)
+#define F16_FI_G3B_STRIDE 4
+#define F16_FI_G3A 3636      // (Cx, Cz, Cm) on DH1 x beta x alpha-cell: 5*19*13 nodes x 3 x (f, d)
+#define F16_FI_G3A_STRIDE 6
+#define F16_FI_G2 11046      // alpha x beta group: 19*13 nodes x 21 tables x (f, d)
+#define F16_FI_G2_STRIDE 42
+#define F16_FI_DOUBLES 21420
+#define F16_FI_BYTES (F16_FI_DOUBLES * 8)
+
+enum F16FastG1 {  // table order inside a G1 cell
+  FG1_Cxq = 0, FG1_dCxq_lef, FG1_Czq, FG1_Cmq, FG1_dCmq_lef, FG1_dCm, FG1_Cyr, FG1_dCyr_lef, FG1_Cyp, FG1_dCyp_lef,
+  FG1_Cnr, FG1_dCnr_lef, FG1_Cnp, FG1_dCnp_lef, FG1_dCnbeta, FG1_Clr, FG1_dClr_lef, FG1_Clp, FG1_dClp_lef, FG1_dClbeta,
+  FG1_COUNT
+};
+enum F16FastG2 {  // table order inside a G2 node
+  FG2_Cx0 = 0, FG2_Cx_lef, FG2_Cz0, FG2_Cz_lef, FG2_Cm0, FG2_Cm_lef,
+  FG2_Cy, FG2_Cy_lef, FG2_Cy_a20, FG2_Cy_a20_lef, FG2_Cy_r30,
+  FG2_Cn0, FG2_Cn_lef, FG2_Cn_a20, FG2_Cn_a20_lef, FG2_Cn_r30,
+  FG2_Cl0, FG2_Cl_lef, FG2_Cl_a20, FG2_Cl_a20_lef, FG2_Cl_r30,
+  FG2_COUNT
+};
+
+// ---------------------------------------------------------------------------------------------------
 // lofi image (doubles), exactly the flat array of f16_lofi_data.inc
 // ---------------------------------------------------------------------------------------------------
 #define F16_LOFI_DAMP 0      // [9][12]

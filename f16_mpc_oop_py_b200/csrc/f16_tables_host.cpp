@@ -5,6 +5,7 @@
 // table (C/hifi_F16_AeroData.c:136-145 and the 42 sibling loaders; breakpoints :7-105).
 #include "f16_tables_host.h"
 
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -266,6 +267,67 @@ void build_hifi_image(const std::vector<double>& p, bool clr_from_file, std::vec
       n[G2_Cn_a20_lef] = at(FT_Cn_a20_lef, 14, ia, ib, 0);
       n[G2_Cl_a20_lef] = at(FT_Cl_a20_lef, 14, ia, ib, 0);
     }
+}
+
+// canonical -> fast image (f16_fast.cuh): per alpha CELL the value at the lower node and the difference to the upper one
+void build_hifi_fast_image(const std::vector<double>& p, bool clr_from_file, std::vector<double>& img) {
+  img.assign(F16_FI_DOUBLES, 0.0);
+  for (int i = 0; i < F16_IMG_NA; i++) img[F16_IMG_A + i] = p[F16_CANON_A1 + i];
+  for (int i = 0; i < F16_N_B; i++) img[F16_IMG_B + i] = p[F16_CANON_B + i];
+  for (int i = 0; i < F16_N_D1; i++) img[F16_IMG_D1 + i] = p[F16_CANON_D1 + i];
+  for (int i = 0; i < F16_N_D2; i++) img[F16_IMG_D2 + i] = p[F16_CANON_D2 + i];
+  auto tab = [&](int t) { return p.data() + canon_table_offset(t); };
+  auto at = [&](int t, int na, int ia, int ib, int id) {
+    // The reference never reads CL1320_ALPHA1_606.dat (hifi_F16_AeroData.c:965-972): as built, CLr == 0.
+    if (t == FT_CLr && !clr_from_file) return 0.0;
+    return tab(t)[(id * F16_N_B + ib) * na + ia];
+  };
+  auto put = [&](double* dst, int t, int na, int ia, int ib, int id) {
+    const double f = at(t, na, ia, ib, id);
+    dst[0] = f;
+    dst[1] = at(t, na, ia + 1, ib, id) - f;
+  };
+  for (int i = 0; i < F16_N_D1 - 1; i++) {
+    img[F16_FI_ETA + 2 * i] = tab(FT_eta_el)[i];
+    img[F16_FI_ETA + 2 * i + 1] = tab(FT_eta_el)[i + 1] - tab(FT_eta_el)[i];
+  }
+  // rho = rho0 * tfac^4.14 (nlplant.c:478): centres c_i = (18.5 + i)/64; entry = (1/(64 c_i), 0.5 rho0 c_i^4.14)
+  for (int i = 0; i < F16_FI_NPOW; i++) {
+    const long double c = (18.5L + i) / 64.0L;
+    img[F16_FI_POW + 2 * i] = (double)(1.0L / (64.0L * c));
+    img[F16_FI_POW + 2 * i + 1] = (double)(0.5L * 2.377e-3L * powl(c, (long double)4.14));
+  }
+  const int g1_src[FG1_COUNT][2] = {
+      {FT_CXq, 20}, {FT_dCXq_lef, 14}, {FT_CZq, 20}, {FT_CMq, 20}, {FT_dCMq_lef, 14}, {FT_dCm, 20}, {FT_CYr, 20},
+      {FT_dCYr_lef, 14}, {FT_CYp, 20}, {FT_dCYp_lef, 14}, {FT_CNr, 20}, {FT_dCNr_lef, 14}, {FT_CNp, 20}, {FT_dCNp_lef, 14},
+      {FT_dCNbeta, 20}, {FT_CLr, 20}, {FT_dCLr_lef, 14}, {FT_CLp, 20}, {FT_dCLp_lef, 14}, {FT_dCLbeta, 20}};
+  for (int ia = 0; ia < F16_FI_NAC; ia++)
+    for (int s = 0; s < FG1_COUNT; s++) put(&img[F16_FI_G1 + ia * F16_FI_G1_STRIDE + 2 * s], g1_src[s][0], g1_src[s][1], ia, 0, 0);
+  for (int id = 0; id < F16_N_D2; id++)
+    for (int ib = 0; ib < F16_N_B; ib++)
+      for (int ia = 0; ia < F16_FI_NAC; ia++) {
+        double* n = &img[F16_FI_G3B + ((id * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3B_STRIDE];
+        put(n + 0, FT_Cn, 20, ia, ib, id);
+        put(n + 2, FT_Cl, 20, ia, ib, id);
+      }
+  for (int id = 0; id < F16_N_D1; id++)
+    for (int ib = 0; ib < F16_N_B; ib++)
+      for (int ia = 0; ia < F16_FI_NAC; ia++) {
+        double* n = &img[F16_FI_G3A + ((id * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3A_STRIDE];
+        put(n + 0, FT_Cx, 20, ia, ib, id);
+        put(n + 2, FT_Cz, 20, ia, ib, id);
+        put(n + 4, FT_Cm, 20, ia, ib, id);
+      }
+  // alpha x beta group; dele = 0 is breakpoint 2 of DH1 and breakpoint 1 of DH2
+  const int g2_src[FG2_COUNT][3] = {
+      {FT_Cx, 20, 2}, {FT_Cx_lef, 14, 0}, {FT_Cz, 20, 2}, {FT_Cz_lef, 14, 0}, {FT_Cm, 20, 2}, {FT_Cm_lef, 14, 0},
+      {FT_Cy, 20, 0}, {FT_Cy_lef, 14, 0}, {FT_Cy_a20, 20, 0}, {FT_Cy_a20_lef, 14, 0}, {FT_Cy_r30, 20, 0},
+      {FT_Cn, 20, 1}, {FT_Cn_lef, 14, 0}, {FT_Cn_a20, 20, 0}, {FT_Cn_a20_lef, 14, 0}, {FT_Cn_r30, 20, 0},
+      {FT_Cl, 20, 1}, {FT_Cl_lef, 14, 0}, {FT_Cl_a20, 20, 0}, {FT_Cl_a20_lef, 14, 0}, {FT_Cl_r30, 20, 0}};
+  for (int ib = 0; ib < F16_N_B; ib++)
+    for (int ia = 0; ia < F16_FI_NAC; ia++)
+      for (int s = 0; s < FG2_COUNT; s++)
+        put(&img[F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE + 2 * s], g2_src[s][0], g2_src[s][1], ia, ib, g2_src[s][2]);
 }
 
 static const double LOFI_DATA[F16_IMG_LOFI_DOUBLES] = {

@@ -13,5 +13,6 @@ bool check_grids(const std::vector<double>& payload, std::string& err);
 void payload_sha256_hex(const std::vector<double>& payload, char out65[65]);
 size_t canon_table_offset(int table_id);
 void build_hifi_image(const std::vector<double>& payload, bool clr_from_file, std::vector<double>& img);
+void build_hifi_fast_image(const std::vector<double>& payload, bool clr_from_file, std::vector<double>& img);
 void build_lofi_image(std::vector<double>& img);
 }  // namespace f16

@@ -6,9 +6,10 @@
 #include <vector>
 
 #include "../../f16_mpc_oop_py_b200/csrc/f16_model.cuh"
+#include "../../f16_mpc_oop_py_b200/csrc/f16_fast.cuh"
 #include "../../f16_mpc_oop_py_b200/csrc/f16_tables_host.h"
 
-static std::vector<double> g_hifi, g_lofi;
+static std::vector<double> g_hifi, g_lofi, g_fast;
 
 extern "C" {
 __attribute__((visibility("default"))) int emu_init(const char* path, int clr_from_file) {
@@ -18,6 +19,7 @@ __attribute__((visibility("default"))) int emu_init(const char* path, int clr_fr
   if (!f16::check_grids(payload, err)) return -2;
   f16::build_hifi_image(payload, clr_from_file != 0, g_hifi);
   f16::build_lofi_image(g_lofi);
+  f16::build_hifi_fast_image(payload, clr_from_file != 0, g_fast);
   return 0;
 }
 
@@ -78,5 +80,47 @@ __attribute__((visibility("default"))) unsigned emu_hifi_probe(double a, double 
   f16::ref_cell(img + F16_IMG_D1, L.d1, e, cl[4], cl[5]);
   f16::ref_cell(img + F16_IMG_D2, L.d2, e, cl[6], cl[7]);
   return 0;
+}
+// the F16_MATH_FAST arithmetic of f16_fast.cuh (hifi step), same control flow as step_hifi_fast_kernel
+__attribute__((visibility("default"))) unsigned emu_calc_xdot_fast(const double* x_, const double* u_, double* xd_, double xcg) {
+  double x[18], u[4], xd[18];
+  for (int i = 0; i < 18; i++) x[i] = x_[i];
+  for (int i = 0; i < 4; i++) u[i] = u_[i];
+  const bool ok = f16::fastmath::calc_xdot_hifi(g_fast.data(), x, u, xcg, xd);
+  for (int i = 0; i < 18; i++) xd_[i] = ok ? xd[i] : __builtin_nan("");
+  return ok ? 0u : f16::hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
+}
+
+__attribute__((visibility("default"))) unsigned emu_step_fast(double* x_, const double* u_, int K, double dt, double xcg,
+                                                              const f16::LqrLaw* lqr, int* steps_done) {
+  double x[18], u_in[4];
+  for (int i = 0; i < 18; i++) x[i] = x_[i];
+  for (int i = 0; i < 4; i++) u_in[i] = u_[i];
+  const bool u_ok = !(f16::either_nan(u_in[0], u_in[1]) || f16::either_nan(u_in[2], u_in[3]));
+  int k = 0;
+  if (u_ok)
+    for (; k < K; k++) {
+      if (!f16::fastmath::step_ok(x)) break;
+      double u[4], xd[18];
+      if (lqr) f16::lqr_action(*lqr, x, u_in, u);
+      else for (int i = 0; i < 4; i++) u[i] = u_in[i];
+      if (!f16::fastmath::calc_xdot_hifi(g_fast.data(), x, u, xcg, xd)) break;
+      for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);
+    }
+  unsigned st = 0;
+  if (k < K) {
+    st = f16::step_bounds(x, u_in);
+    if (!st) st = f16::hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
+  }
+  for (int i = 0; i < 18; i++) x_[i] = x[i];
+  if (steps_done) *steps_done = k;
+  return st;
+}
+
+// accuracy probes of the fast elementary functions: out = {sin, cos (sincos_any), sin, cos (sincos_quarter), half_rho}
+__attribute__((visibility("default"))) void emu_fastmath_probe(double x, double tfac, double* out) {
+  f16::fastmath::sincos_any(x, out[0], out[1]);
+  f16::fastmath::sincos_quarter(x, out[2], out[3]);
+  out[4] = f16::fastmath::half_rho(g_fast.data(), tfac);
 }
 }

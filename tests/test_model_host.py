@@ -129,3 +129,121 @@ def test_envelope_status_equal(emu, oracle):
             s = emu.emu_nlplant(_p(np.ascontiguousarray(xu[:, i])), _p(xd), fi, 0.25)
             assert s == int(st[i])
             assert np.array_equal(xd, ref[:, i], equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F16_MATH_FAST arithmetic (csrc/f16_fast.cuh): re-associated, so compared with a tolerance instead of bit-for-bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_fast(emu):
+    emu.emu_calc_xdot_fast.argtypes = [dp, dp, dp, ctypes.c_double]
+    emu.emu_step_fast.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(LqrLaw),
+                                  ctypes.POINTER(ctypes.c_int)]
+    emu.emu_fastmath_probe.argtypes = [ctypes.c_double, ctypes.c_double, dp]
+    return emu
+
+
+def test_fast_elementary_functions(emu_fast):
+    import mpmath as mp
+    mp.mp.prec = 200
+    r = np.random.default_rng(3)
+    out = np.zeros(5)
+    worst = np.zeros(3)
+    xs = np.concatenate([r.uniform(-np.pi / 4, np.pi / 4, 400), [0.0, np.pi / 4, -np.pi / 4, 1e-300, 1e-9]])
+    for x in xs:                                    # sincos_quarter on its domain
+        emu_fast.emu_fastmath_probe(float(x), 0.9, _p(out))
+        worst[0] = max(worst[0], abs(out[2] - float(mp.sin(x))) / max(abs(float(mp.sin(x))), 1e-300) if x else abs(out[2]),
+                       abs(out[3] - float(mp.cos(x))))
+    xs = np.concatenate([r.uniform(-700, 700, 600), r.uniform(-7, 7, 400), np.arange(-8, 9) * np.pi / 2, [9.9e4, -9.9e4, 2e5]])
+    for x in xs:                                    # sincos_any: absolute error (values are <= 1)
+        emu_fast.emu_fastmath_probe(float(x), 0.9, _p(out))
+        worst[1] = max(worst[1], abs(out[0] - float(mp.sin(mp.mpf(float(x))))), abs(out[1] - float(mp.cos(mp.mpf(float(x))))))
+    alts = np.concatenate([r.uniform(0, 100000, 500), [0.0, 100000.0, 35000.0]])
+    for alt in alts:                                # half_rho = 0.5 * 2.377e-3 * tfac^4.14 (nlplant.c:478)
+        tfac = 1 - .703e-5 * alt
+        emu_fast.emu_fastmath_probe(0.1, float(tfac), _p(out))
+        ref = float(mp.mpf(0.5) * mp.mpf(2.377e-3) * mp.mpf(float(tfac)) ** mp.mpf(4.14))
+        worst[2] = max(worst[2], abs(out[4] - ref) / ref)
+    assert worst[0] < 3e-16 and worst[1] < 3e-16 and worst[2] < 6e-16, worst
+
+
+@pytest.mark.parametrize("xcg", [0.25, 0.35])
+def test_fast_calc_xdot_within_tolerance(emu_fast, oracle, xcg):
+    """<= 1e-12 of max(|ref|, rms of that derivative) on random in-envelope states and on perturbed-trim states."""
+    from _inputs import X_TRIM_XCG25, perturbed_trim
+    from conftest import scaled_err
+    xu = random_envelope_xu(3000, seed=21, hifi=True)
+    r = np.random.default_rng(4)
+    x = np.vstack([xu, r.uniform(-30, 30, (1, xu.shape[1]))])          # lf1
+    x[2] = r.uniform(0, 60000, xu.shape[1])                            # altitude both sides of 35000 ft
+    u = np.stack([r.uniform(500, 20000, 3000), r.uniform(-30, 30, 3000), r.uniform(-25, 25, 3000), r.uniform(-35, 35, 3000)])
+    xp, up = perturbed_trim(3000, X_TRIM_XCG25, seed=8)
+    for X, U in ((x, u), (xp, up)):
+        ref, st = oracle.calc_xdot_batch(X, U, 1, xcg, PORT)
+        out = np.empty_like(ref)
+        for i in range(X.shape[1]):
+            xd = np.zeros(18)
+            s = emu_fast.emu_calc_xdot_fast(_p(np.ascontiguousarray(X[:, i])), _p(np.ascontiguousarray(U[:, i])), _p(xd), xcg)
+            assert s == int(st[i])
+            out[:, i] = xd
+        assert (st == 0).all()
+        assert scaled_err(out, ref) < 1e-12
+
+
+def test_fast_step_trajectory_and_status(emu_fast, oracle):
+    """10 s of Euler from perturbed trim: <= 1e-9 scaled; aircraft that leave the envelope stop at the same step with
+    the same status word (or, within rounding of a threshold, one step apart)."""
+    from _inputs import X_TRIM_XCG25, X_TRIM_XCG35, perturbed_trim
+    from conftest import scaled_err
+    for xt, xcg, n, K in ((X_TRIM_XCG25, 0.25, 6, 10000), (X_TRIM_XCG35, 0.35, 12, 6000)):
+        x0, u0 = perturbed_trim(n, xt, seed=13)
+        ref, st = oracle.step_batch(x0, u0, K, 0.001, 1, xcg, None, PORT)
+        out = np.empty_like(ref)
+        sts = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            x = np.ascontiguousarray(x0[:, i])
+            sts[i] = emu_fast.emu_step_fast(_p(x), _p(np.ascontiguousarray(u0[:, i])), K, 0.001, xcg, None, None)
+            out[:, i] = x
+        assert np.array_equal(sts, st)
+        alive = st == 0
+        assert alive.any()
+        assert scaled_err(out[:, alive], ref[:, alive]) < 1e-9
+        if (~alive).any():      # frozen aircraft: stopped in the same state up to the accumulated rounding
+            assert scaled_err(out[:, ~alive], ref[:, ~alive]) < 1e-6
+
+
+def test_fast_closed_loop_step(emu_fast, oracle):
+    from conftest import scaled_err
+    g = load_golden("xcg35")
+    r = np.random.default_rng(9)
+    K = 0.05 * r.normal(size=(3, 9))
+    sel = list(g["mpc_x_idx"])
+    law = make_lqr(K, sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+    x0 = g["xs"][3].copy()
+    ref, st = oracle.step_batch(x0[:, None].copy(), g["u_trim"][:, None].copy(), 300, 0.001, 1, 0.35, law)
+    x = x0.copy()
+    assert emu_fast.emu_step_fast(_p(x), _p(g["u_trim"].copy()), 300, 0.001, 0.35, ctypes.byref(law), None) == int(st[0])
+    assert scaled_err(x[:, None], ref) < 1e-10
+
+
+def test_fast_step_status_words(emu_fast, oracle):
+    """Every way of stopping reports the oracle's status word and freezes the same state."""
+    from _inputs import X_TRIM_XCG25
+    cases = []
+    for idx, val in ((2, -1.0), (2, 100001.0), (6, 901.0), (8, 31.0), (9, -301.0), (12, 999.0), (13, 25.5), (14, -21.6),
+                     (15, 30.5), (16, 25.5), (16, -0.1), (7, np.deg2rad(46.0)), (7, np.deg2rad(-20.5)), (8, np.deg2rad(30.5)),
+                     (3, np.nan), (17, np.nan), (6, np.nan), (0, np.nan)):
+        x = X_TRIM_XCG25.copy()
+        x[idx] = val
+        cases.append(x)
+    X = np.ascontiguousarray(np.array(cases).T)
+    U = np.ascontiguousarray(np.tile(X_TRIM_XCG25[12:16][:, None], (1, X.shape[1])))
+    U[1, 3] = np.nan
+    ref, st = oracle.step_batch(X, U, 5, 0.001, 1, 0.25, None, PORT)
+    for i in range(X.shape[1]):
+        x = np.ascontiguousarray(X[:, i])
+        done = ctypes.c_int(-1)
+        s = emu_fast.emu_step_fast(_p(x), _p(np.ascontiguousarray(U[:, i])), 5, 0.001, 0.25, None, ctypes.byref(done))
+        assert s == int(st[i]) and s != 0, (i, s, int(st[i]))
+        assert done.value == 0
+        assert np.array_equal(x, ref[:, i], equal_nan=True)
