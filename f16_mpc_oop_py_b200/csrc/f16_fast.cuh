@@ -32,12 +32,22 @@
 namespace f16 {
 namespace fastmath {
 
-// Constant-bank operands.  sin/cos kernels on [-pi/4, pi/4]: the classic fdlibm minimax coefficients.
+// Constant-bank operands (one LDCU.64 each instead of two UMOV immediates).  sin/cos kernels on [-pi/4, pi/4]:
+// the classic fdlibm minimax coefficients.
 struct K_t {
   double S[6], C[6];
   double two_over_pi, pio2_hi, pio2_mid;
   double PW[9];  // binomial coefficients C(4.14, k), k = 1..9
+  double r2d, shrink, inv15, c5_3, c7_3, tlapse, inv21_5, inv30, ninv25, half_cbar, g, S_m, inv_m, lef_q, inv_pi,
+      c1_38, c1_45, c20_2, inv0_136, ixx_qr, ixx_pq, ixx_l, ixx_n, iyy_pr, iyy_p2, inv_Jy, izz_n, izz_l, izz_pq, izz_qr,
+      xcg_arm;
 };
+// inertia terms of nlplant.c:413-436 pre-divided by (Jx Jz - Jxz^2) resp. Jy
+#define F16_JX 9496.0
+#define F16_JY 55814.0
+#define F16_JZ 63100.0
+#define F16_JXZ 982.0
+#define F16_JD (F16_JX * F16_JZ - F16_JXZ * F16_JXZ)
 F16_KCONST K_t K = {
     {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,
      -2.50507602534068634195e-08, 1.58969099521155010221e-10},
@@ -45,7 +55,16 @@ F16_KCONST K_t K = {
      2.08757232129817482790e-09, -1.13596475577881948265e-11},
     0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17,
     {4.14, 6.499799999999999, 4.636523999999999, 1.321409339999999, 0.036999461519999895, -0.005303256151199987,
-     0.0014091509201759967, -0.0005037714539629189, 0.00021606197914409635}};
+     0.0014091509201759967, -0.0005037714539629189, 0.00021606197914409635},
+    180.0 / 3.141592653589793, 1.0 - 1.0 / 1073741824.0, 1.0 / 15.0, 5.0 / 3.0, 7.0 / 3.0, -.703e-5, 1.0 / 21.5, 1.0 / 30.0,
+    -1.0 / 25.0, 0.5 * 11.32, 32.17, 300.0 / 636.94, 1.0 / 636.94, 0.5 * 9.05 / 1715.0, 1.0 / 3.141592653589793,
+    1.38, 1.45, 20.2, 1 / 0.136,
+    -(F16_JZ * (F16_JZ - F16_JY) + F16_JXZ * F16_JXZ) / F16_JD, F16_JXZ * (F16_JX - F16_JY + F16_JZ) / F16_JD,
+    F16_JZ / F16_JD, F16_JXZ / F16_JD,
+    (F16_JZ - F16_JX) / F16_JY, -F16_JXZ / F16_JY, 1.0 / F16_JY,
+    F16_JX / F16_JD, F16_JXZ / F16_JD, (F16_JX * (F16_JX - F16_JY) + F16_JXZ * F16_JXZ) / F16_JD,
+    -F16_JXZ * (F16_JX - F16_JY + F16_JZ) / F16_JD,
+    11.32 / 30.0};
 
 F16_FD int lo32(double v) {
 #if defined(__CUDA_ARCH__)
@@ -54,6 +73,15 @@ F16_FD int lo32(double v) {
   long long b;
   __builtin_memcpy(&b, &v, 8);
   return (int)(b & 0xffffffffLL);
+#endif
+}
+F16_FD int hi32(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(v);
+#else
+  long long b;
+  __builtin_memcpy(&b, &v, 8);
+  return (int)(b >> 32);
 #endif
 }
 F16_FD double flip_sign(double v, int mask_hi) {  // mask_hi = 0 or 0x80000000
@@ -85,14 +113,8 @@ F16_FD void sincos_quarter(double x, double& s, double& c) {
   c = fma(z, fma(z, pc, -0.5), 1.0);
 }
 
-#if defined(__CUDACC__)
-__device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
-#else
-static void sincos_slow(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
-#endif
-
-// sin and cos of any argument: j = rint(x 2/pi), r = x - j pi/2 in two FMAs, quadrant fix-up on the sign bits.
-// |x| > 1e5 (never reached by a bounded flight state) takes libm's path.
+// sin and cos for |x| < 2^30: j = rint(x 2/pi), r = x - j pi/2 in two FMAs (|j| (pi/2 - hi - mid)| < 1e-23), quadrant
+// fix-up on the sign bits; straight-line code.  Larger arguments never reach this function (angles_ok()).
 F16_FD void sincos_any(double x, double& s, double& c) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fma(x, K.two_over_pi, magic);
@@ -100,10 +122,6 @@ F16_FD void sincos_any(double x, double& s, double& c) {
   const int q = lo32(t);
   double r = fma(-j, K.pio2_hi, x);
   r = fma(-j, K.pio2_mid, r);
-  if (fabs(x) > 1.0e5) {
-    sincos_slow(x, &s, &c);
-    return;
-  }
   double ss, cc;
   sincos_quarter(r, ss, cc);
   const bool sw = (q & 1) != 0;
@@ -111,6 +129,12 @@ F16_FD void sincos_any(double x, double& s, double& c) {
   s = flip_sign(s0, (q & 2) << 30);
   c = flip_sign(c0, ((q + 1) & 2) << 30);
 }
+
+#if defined(__CUDACC__)
+__device__ __noinline__ void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
+#else
+static void sincos_libm(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+#endif
 
 // 0.5 * rho0 * tfac^4.14 for tfac in [0.28125, 1.03125): table of centres + binomial series (15 FP64 instructions)
 F16_FD double half_rho(const double* img, double tfac) {
@@ -134,7 +158,33 @@ F16_FD double half_rho(const double* img, double tfac) {
   return p * e.y;
 }
 
-F16_FD double rcp(double v) { return 1.0 / v; }
+// 1/v for a well-scaled positive or negative v: hardware seed + two Newton steps, no special-case path
+F16_FD double rcp_nr(double v) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  double e = fma(-v, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-v, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+#else
+  return 1.0 / v;
+#endif
+}
+
+// cell and weight on a piecewise-uniform axis.  u = position in cell units (cell k spans [k, k+1], n cells).
+// floor(u) through the round-to-nearest of (u (1 - 2^-30) - 0.5) + 1.5*2^52: no conversion instruction, no
+// breakpoint load, and u == n lands in the last cell.  Within 2^-30 of a breakpoint the neighbouring cell may be
+// chosen with a weight just outside [0, 1]: the interpolant is continuous there, so the value moves by rounding only.
+F16_FD int cell_of(double u, int n_cells, double& lam) {
+  const double magic = 6755399441055744.0;
+  const double tm = fma(u, K.shrink, -0.5) + magic;
+  lam = u - (tm - magic);
+  int k = lo32(tm);
+  k = k < 0 ? 0 : (k > n_cells - 1 ? n_cells - 1 : k);  // memory safety only; never active for in-envelope u
+  return k;
+}
 
 // value of table `slot` of an (f, d) node at alpha weight la
 F16_FD double fd(const double* node, int slot, double la) {
@@ -143,61 +193,89 @@ F16_FD double fd(const double* node, int slot, double la) {
 }
 F16_FD double mix(double lam, double lo, double hi) { return fma(lam, hi - lo, lo); }
 
-// cheap "any violation" form of env.py:117 + the NaN rule of step_bounds(): true when every bounded state is
-// inside its closed interval (a NaN fails the comparison) and no unbounded state is NaN
+// |v| < 2^30 and not NaN, on the integer pipe
+F16_FD bool small_angle(double v) { return (hi32(v) & 0x7fffffff) < 0x41d00000; }
+
+// "all inside" form of env.py:117 + the NaN rule of step_bounds(): true when every bounded state is inside its
+// closed interval (a NaN fails the comparison), no unbounded state is NaN, and (LIBM_TRIG == false) the three
+// Euler angles are small enough for sincos_any().
+template <bool LIBM_TRIG>
 F16_FD bool step_ok(const double (&x)[18]) {
-  bool ok = (x[2] >= 0.0) && (x[2] <= 100000.0);
-  ok = ok && (x[6] >= 0.0) && (x[6] <= 900.0);
-  ok = ok && (x[7] >= -20.0) && (x[7] <= 90.0);
-  ok = ok && (fabs(x[8]) <= 30.0) && (fabs(x[9]) <= 300.0) && (fabs(x[10]) <= 100.0) && (fabs(x[11]) <= 50.0);
-  ok = ok && (x[12] >= 1000.0) && (x[12] <= 19000.0);
-  ok = ok && (fabs(x[13]) <= 25.0) && (fabs(x[14]) <= 21.5) && (fabs(x[15]) <= 30.0);
-  ok = ok && (x[16] >= 0.0) && (x[16] <= 25.0);
-  ok = ok && !either_nan(x[0], x[1]) && !either_nan(x[3], x[4]) && !either_nan(x[5], x[17]);
+  bool ok = (x[2] >= 0.0) & (x[2] <= 100000.0);
+  ok &= (x[6] >= 0.0) & (x[6] <= 900.0);
+  ok &= (x[7] >= -20.0) & (x[7] <= 90.0);
+  ok &= (fabs(x[8]) <= 30.0) & (fabs(x[9]) <= 300.0) & (fabs(x[10]) <= 100.0) & (fabs(x[11]) <= 50.0);
+  ok &= (x[12] >= 1000.0) & (x[12] <= 19000.0);
+  ok &= (fabs(x[13]) <= 25.0) & (fabs(x[14]) <= 21.5) & (fabs(x[15]) <= 30.0);
+  ok &= (x[16] >= 0.0) & (x[16] <= 25.0);
+  ok &= !either_nan(x[0], x[1]) & !either_nan(x[17], x[17]);
+  if (LIBM_TRIG) ok &= !either_nan(x[3], x[4]) & !either_nan(x[5], x[5]);
+  else ok &= small_angle(x[3]) & small_angle(x[4]) & small_angle(x[5]);
   return ok;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// env.py::_calc_xdot (env.py:65-103) for the hifi model, all 18 derivatives.  `img` is the fast image.
-// Precondition (checked by the caller through step_ok): states inside parameters.py bounds, no NaN.
-// Returns false when alpha / beta leave the hifi tables (the caller then reports the exact status word).
-// ------------------------------------------------------------------------------------------------------
-F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&u)[4], double xcg, double (&xd)[18]) {
-  const double g = 32.17, m = 636.94, B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
-  const double r2d = 180.0 / 3.141592653589793;
-  const double Jy = 55814.0, Jxz = 982.0, Jz = 63100.0, Jx = 9496.0;
+// utils.py:308-330 command saturation (loop-invariant in open loop)
+F16_FD void clip_commands(const double (&u)[4], double (&uc)[4]) {
+  uc[0] = clipd(u[0], 1000, 19000);
+  uc[1] = clipd(u[1], -25, 25);
+  uc[2] = clipd(u[2], -21.5, 21.5);
+  uc[3] = clipd(u[3], -30, 30);
+}
 
-  const double alpha = x[7] * r2d, beta = x[8] * r2d, el = x[13];
-  // hifi_envelope(): elevator range is already guaranteed by the |x[13]| <= 25 bound
-  if (!((alpha >= -20.0) && (alpha <= 45.0) && (fabs(beta) <= 30.0))) return false;
+// ------------------------------------------------------------------------------------------------------
+// env.py::_calc_xdot (env.py:65-103) for the hifi model, all 18 derivatives.  `img` is the fast image, `uc` the
+// saturated commands.  Precondition (checked by the caller through step_ok): states inside parameters.py bounds,
+// no NaN.  Returns false when alpha / beta leave the hifi tables (the caller then reports the exact status word).
+// ------------------------------------------------------------------------------------------------------
+template <bool LIBM_TRIG>
+F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
+  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
 
-  const AxisLoc La = locate_alpha(img, alpha), Lb = locate_beta(img, beta), L1 = locate_dh1(img, el),
-                L2 = locate_dh2(img, el);
-  const double la = La.lam, lb = Lb.lam, l1 = L1.lam, l2 = L2.lam;
+  const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
+  // hifi_envelope(): the elevator range is already guaranteed by the |x[13]| <= 25 bound
+  if (!((alpha >= -20.0) & (alpha <= 45.0) & (fabs(beta) <= 30.0))) return false;
+
+  // cells (ALPHA -20:5:45; BETA1 -30:5:-10:2:10:5:30; DH1 -25,-10,0,10,25; DH2 -25,0,25 -- check_grids() verifies)
+  double la, lb, l1, l2;
+  const int ia = cell_of(fma(alpha, 0.2, 4.0), 13, la);
+  const bool b_out = (beta < -10.0) | (beta >= 10.0);
+  const int ib = cell_of(fma(beta, b_out ? 0.2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
+  const bool e_out = (el < -10.0) | (el >= 10.0);
+  const int i1 = cell_of(fma(el, e_out ? K.inv15 : 0.1, el < -10.0 ? K.c5_3 : (el >= 10.0 ? K.c7_3 : 2.0)), 4, l1);
+  const int i2 = cell_of(fma(el, 0.04, 1.0), 2, l2);
 
   double sa, ca, sb, cb, st, ct, sphi, cphi, spsi, cpsi;
   sincos_quarter(x[7], sa, ca);
   sincos_quarter(x[8], sb, cb);
-  sincos_any(x[4], st, ct);
-  sincos_any(x[3], sphi, cphi);
-  sincos_any(x[5], spsi, cpsi);
+  if (LIBM_TRIG) {
+    sincos_libm(x[4], &st, &ct);
+    sincos_libm(x[3], &sphi, &cphi);
+    sincos_libm(x[5], &spsi, &cpsi);
+  } else {
+    sincos_any(x[4], st, ct);
+    sincos_any(x[3], sphi, cphi);
+    sincos_any(x[5], spsi, cpsi);
+  }
 
   double vt = x[6];
   if (vt <= 0.01) vt = 0.01;  // nlplant.c:104
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
 
   // atmos, nlplant.c:467-490: only qbar (Nlplant) and qbar/ps (upd_lef, utils.py:291-296) are consumed here
-  const double tfac = fma(-.703e-5, x[2], 1.0);
+  const double tfac = fma(K.tlapse, x[2], 1.0);
   const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
-  const double hrho = half_rho(img, tfac);
-  const double qbar = hrho * (vt * vt);
-  const double inv_temp = rcp(temp), inv_vt = rcp(vt), inv_ct = rcp(ct), inv_cb = rcp(cb);
+  const double qbar = half_rho(img, tfac) * (vt * vt);
+  // one reciprocal for 1/(vt cb), 1/vt, 1/ct and 1/temp
+  const double vc = vt * cb, tc = ct * temp;
+  const double rr = rcp_nr(vc * tc);
+  const double inv_vc = rr * tc, inv_tc = rr * vc;
+  const double inv_vt = inv_vc * cb, inv_ct = inv_tc * temp, inv_temp = inv_tc * ct;
 
-  const double dail = x[14] * (1.0 / 21.5), drud = x[15] * (1.0 / 30.0);  // nlplant.c:123-124
-  const double dlef = fma(x[16], -(1.0 / 25.0), 1.0);                      // nlplant.c:125
+  const double dail = x[14] * K.inv21_5, drud = x[15] * K.inv30;  // nlplant.c:123-124
+  const double dlef = fma(x[16], K.ninv25, 1.0);                    // nlplant.c:125
 
   // navigation + kinematics, nlplant.c:148-176
-  const double U = vt * ca * cb, V = vt * sb, W = vt * sa * cb;
+  const double U = vc * ca, V = vt * sb, W = vc * sa;
   xd[0] = U * (ct * cpsi) + V * (sphi * cpsi * st - cphi * spsi) + W * (cphi * st * cpsi + sphi * spsi);
   xd[1] = U * (ct * spsi) + V * (sphi * spsi * st + cphi * cpsi) + W * (cphi * st * spsi - sphi * cpsi);
   xd[2] = U * st - V * (sphi * ct) - W * (cphi * ct);
@@ -207,10 +285,10 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   xd[5] = qr * inv_ct;
 
   // weights of the damping terms, nlplant.c:333-377
-  const double qQ = (0.5 * cbar) * inv_vt * Q, bR = (0.5 * B) * inv_vt * R, bP = (0.5 * B) * inv_vt * P;
+  const double qQ = K.half_cbar * inv_vt * Q, bR = (0.5 * B) * inv_vt * R, bP = (0.5 * B) * inv_vt * P;
 
   double Cx_tot, Cz_tot, Cm_tot, Cy_tot, Cn_tot, Cl_tot;
-  double dCz_lef, Czq_dyn;
+  double dCz_lef;
 
   // ---- alpha x beta group (hifi_C_lef, hifi_rudder, hifi_ailerons: hifi:1892-1926) ----
   {
@@ -219,7 +297,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
     const double w_a20 = dail - w_a;           // C_a20
     const double w_lef = dlef - w_a;           // C_lef
     const double w_0 = -(w_lef + w_a20 + w_a + drud);  // the dele = 0 slice subtracted by every delta
-    const double* n0 = img + F16_FI_G2 + (Lb.lo * F16_FI_NAC + La.lo) * F16_FI_G2_STRIDE;
+    const double* n0 = img + F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE;
     const double* n1 = n0 + F16_FI_NAC * F16_FI_G2_STRIDE;
     double dx[2], dz[2], dm[2], y[2], n[2], l[2];
 #if defined(__CUDA_ARCH__)
@@ -255,7 +333,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   }
   // ---- alpha x beta x DH2: Cn, Cl (hifi:1876-1877) ----
   {
-    const double* p = img + F16_FI_G3B + ((L2.lo * F16_N_B + Lb.lo) * F16_FI_NAC + La.lo) * F16_FI_G3B_STRIDE;
+    const double* p = img + F16_FI_G3B + ((i2 * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3B_STRIDE;
     const int sb_ = F16_FI_NAC * F16_FI_G3B_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3B_STRIDE;
     const double n_lo = mix(lb, fd(p, 0, la), fd(p + sb_, 0, la)), n_hi = mix(lb, fd(p + sd, 0, la), fd(p + sd + sb_, 0, la));
     const double l_lo = mix(lb, fd(p, 1, la), fd(p + sb_, 1, la)), l_hi = mix(lb, fd(p + sd, 1, la), fd(p + sd + sb_, 1, la));
@@ -265,7 +343,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   // ---- alpha x beta x DH1: Cx, Cz, Cm (hifi:1872-1874) and eta_el (hifi:1932) ----
   double Cm3;
   {
-    const double* p = img + F16_FI_G3A + ((L1.lo * F16_N_B + Lb.lo) * F16_FI_NAC + La.lo) * F16_FI_G3A_STRIDE;
+    const double* p = img + F16_FI_G3A + ((i1 * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3A_STRIDE;
     const int sb_ = F16_FI_NAC * F16_FI_G3A_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3A_STRIDE;
     const double x_lo = mix(lb, fd(p, 0, la), fd(p + sb_, 0, la)), x_hi = mix(lb, fd(p + sd, 0, la), fd(p + sd + sb_, 0, la));
     const double z_lo = mix(lb, fd(p, 1, la), fd(p + sb_, 1, la)), z_hi = mix(lb, fd(p + sd, 1, la), fd(p + sd + sb_, 1, la));
@@ -273,16 +351,15 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
     Cx_tot += mix(l1, x_lo, x_hi);
     Cz_tot = fma(dCz_lef, dlef, mix(l1, z_lo, z_hi));
     Cm3 = mix(l1, m_lo, m_hi);
-    const d2 e = ld2(img + F16_FI_ETA + 2 * L1.lo);
+    const d2 e = ld2(img + F16_FI_ETA + 2 * i1);
     Cm3 *= fma(l1, e.y, e.x);
   }
   // ---- alpha-only group: damping, lef damping, other (hifi:1880-1890,1901-1911,1928-1934) ----
   {
-    const double* p = img + F16_FI_G1 + La.lo * F16_FI_G1_STRIDE;
+    const double* p = img + F16_FI_G1 + ia * F16_FI_G1_STRIDE;
     Cx_tot = fma(qQ, fma(fd(p, FG1_dCxq_lef, la), dlef, fd(p, FG1_Cxq, la)), Cx_tot);
     // nlplant.c:339 uses delta_Cz_lef where delta_Czq_lef was meant -- reproduced
-    Czq_dyn = fma(dCz_lef, dlef, fd(p, FG1_Czq, la));
-    Cz_tot = fma(qQ, Czq_dyn, Cz_tot);
+    Cz_tot = fma(qQ, fma(dCz_lef, dlef, fd(p, FG1_Czq, la)), Cz_tot);
     Cm_tot += Cm3 + fd(p, FG1_dCm, la);
     Cm_tot = fma(qQ, fma(fd(p, FG1_dCmq_lef, la), dlef, fd(p, FG1_Cmq, la)), Cm_tot);
     Cm_tot = fma(Cz_tot, xcgr - xcg, Cm_tot);
@@ -291,44 +368,93 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
     Cn_tot = fma(bR, fma(fd(p, FG1_dCnr_lef, la), dlef, fd(p, FG1_Cnr, la)), Cn_tot);
     Cn_tot = fma(bP, fma(fd(p, FG1_dCnp_lef, la), dlef, fd(p, FG1_Cnp, la)), Cn_tot);
     Cn_tot = fma(fd(p, FG1_dCnbeta, la), beta, Cn_tot);
-    Cn_tot = fma(Cy_tot, -(xcgr - xcg) * (cbar / B), Cn_tot);
+    Cn_tot = fma(Cy_tot, (xcg - xcgr) * K.xcg_arm, Cn_tot);
     Cl_tot = fma(bR, fma(fd(p, FG1_dClr_lef, la), dlef, fd(p, FG1_Clr, la)), Cl_tot);
     Cl_tot = fma(bP, fma(fd(p, FG1_dClp_lef, la), dlef, fd(p, FG1_Clp, la)), Cl_tot);
     Cl_tot = fma(fd(p, FG1_dClbeta, la), beta, Cl_tot);
   }
 
   // body-axis accelerations, nlplant.c:383-387
-  const double qS_m = qbar * (S / m);
-  const double Udot = R * V - Q * W - g * st + qS_m * Cx_tot + T * (1.0 / m);
-  const double Vdot = P * W - R * U + g * ct * sphi + qS_m * Cy_tot;
-  const double Wdot = Q * U - P * V + g * ct * cphi + qS_m * Cz_tot;
+  const double qS_m = qbar * K.S_m;
+  const double gct = K.g * ct;
+  const double Udot = fma(T, K.inv_m, fma(qS_m, Cx_tot, fma(-K.g, st, R * V - Q * W)));
+  const double Vdot = fma(qS_m, Cy_tot, fma(gct, sphi, P * W - R * U));
+  const double Wdot = fma(qS_m, Cz_tot, fma(gct, cphi, Q * U - P * V));
   // nlplant.c:393-405 with U = vt ca cb, V = vt sb, W = vt sa cb substituted (vt cancels)
-  const double vtd = ca * cb * Udot + sb * Vdot + sa * cb * Wdot;
+  const double vtd = fma(ca * cb, Udot, fma(sb, Vdot, sa * cb * Wdot));
   xd[6] = vtd;
-  xd[7] = (ca * Wdot - sa * Udot) * (inv_vt * inv_cb);
-  xd[8] = (Vdot - sb * vtd) * (inv_vt * inv_cb);
+  xd[7] = (ca * Wdot - sa * Udot) * inv_vc;
+  xd[8] = fma(-sb, vtd, Vdot) * inv_vc;
 
-  // moments, nlplant.c:413-436 (Heng = 0)
+  // moments, nlplant.c:413-436 (Heng = 0), inertia ratios folded into constants
   const double qSb = qbar * (S * B);
   const double L_tot = Cl_tot * qSb, N_tot = Cn_tot * qSb, M_tot = Cm_tot * (qbar * (S * cbar));
-  const double denom = Jx * Jz - Jxz * Jxz;
-  xd[9] = (Jz * L_tot + Jxz * N_tot - (Jz * (Jz - Jy) + Jxz * Jxz) * (Q * R) + (Jxz * (Jx - Jy + Jz)) * (P * Q)) * (1.0 / denom);
-  xd[10] = (M_tot + (Jz - Jx) * (P * R) - Jxz * (P * P - R * R)) * (1.0 / Jy);
-  xd[11] = (Jx * N_tot + Jxz * L_tot + (Jx * (Jx - Jy) + Jxz * Jxz) * (P * Q) - (Jxz * (Jx - Jy + Jz)) * (Q * R)) * (1.0 / denom);
+  const double PQ = P * Q, QR = Q * R;
+  xd[9] = fma(K.ixx_l, L_tot, fma(K.ixx_n, N_tot, fma(K.ixx_qr, QR, K.ixx_pq * PQ)));
+  xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * (P * P - R * R)));
+  xd[11] = fma(K.izz_n, N_tot, fma(K.izz_l, L_tot, fma(K.izz_pq, PQ, K.izz_qr * QR)));
 
   // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)
-  const double atmos_out = (x[6] * x[6]) * inv_temp * (0.5 * 9.05 / 1715.0);
-  const double alpha_deg = (x[7] * 180.0) * (1.0 / 3.141592653589793);
+  const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
+  const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
   const double lf_in = fma(2.0, alpha_deg, x[17]);
-  double lef_cmd = fma(lf_in, 1.38, 1.45) - atmos_out;
+  double lef_cmd = fma(lf_in, K.c1_38, K.c1_45) - atmos_out;
   lef_cmd = clipd(lef_cmd, 0, 25);
-  xd[12] = clipd(clipd(u[0], 1000, 19000) - x[12], -10000, 10000);
-  xd[13] = clipd(20.2 * (clipd(u[1], -25, 25) - x[13]), -60, 60);
-  xd[14] = clipd(20.2 * (clipd(u[2], -21.5, 21.5) - x[14]), -80, 80);
-  xd[15] = clipd(20.2 * (clipd(u[3], -30, 30) - x[15]), -120, 120);
-  xd[16] = clipd((1 / 0.136) * (lef_cmd - x[16]), -25, 25);
+  xd[12] = clipd(uc[0] - x[12], -10000, 10000);
+  xd[13] = clipd(K.c20_2 * (uc[1] - x[13]), -60, 60);
+  xd[14] = clipd(K.c20_2 * (uc[2] - x[14]), -80, 80);
+  xd[15] = clipd(K.c20_2 * (uc[3] - x[15]), -120, 120);
+  xd[16] = clipd(K.inv0_136 * (lef_cmd - x[16]), -25, 25);
   xd[17] = (alpha_deg - lf_in) * 7.25;
   return true;
+}
+
+// K fused Euler steps of env.py::step from step k; stops (k < K on return) at the first state that fails step_ok or
+// leaves the tables.  The state is not advanced on the failing step.
+template <bool LQR, bool LIBM_TRIG>
+F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrLaw* lqr, double xcg, double dt,
+                     int k, int K) {
+  double uc[4];
+  if (!LQR) clip_commands(u_in, uc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (; k < K; k++) {
+    if (!step_ok<LIBM_TRIG>(x)) break;  // env.py:117 -- the reference exit()s here; we freeze this aircraft
+    double xd[18];
+    if (LQR) {
+      double u[4];
+      lqr_action(*lqr, x, u_in, u);
+      clip_commands(u, uc);
+    }
+    if (!calc_xdot_hifi<LIBM_TRIG>(img, x, uc, xcg, xd)) break;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);  // env.py:126
+  }
+  return k;
+}
+
+F16_FD unsigned exact_status(const double (&x)[18], const double (&u_in)[4]) {
+  unsigned st = step_bounds(x, u_in);
+  if (!st) st = hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
+  return st;
+}
+
+// the whole step_batch semantics for one aircraft: returns the status word, k = steps taken
+template <bool LQR>
+F16_FD unsigned step_aircraft(const double* img, double (&x)[18], const double (&u_in)[4], const LqrLaw* lqr, double xcg,
+                              double dt, int K, int& k) {
+  k = 0;
+  if (either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3])) return K > 0 ? step_bounds(x, u_in) : 0u;
+  k = run_steps<LQR, false>(img, x, u_in, lqr, xcg, dt, 0, K);
+  if (k == K) return 0u;
+  unsigned st = exact_status(x, u_in);  // stopped early: the exact status word of the frozen state
+  if (st) return st;
+  // none of the reference's stop conditions: an Euler angle beyond 2^30 rad -- carry on with libm's trig
+  k = run_steps<LQR, true>(img, x, u_in, lqr, xcg, dt, k, K);
+  return k == K ? 0u : exact_status(x, u_in);
 }
 
 }  // namespace fastmath

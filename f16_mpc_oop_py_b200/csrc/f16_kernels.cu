@@ -229,29 +229,8 @@ step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
 #pragma unroll
     for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
     const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
-    const bool u_ok = !(either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3]));
-    int k = 0;
-    if (u_ok) {
-#pragma unroll 1
-      for (; k < K; k++) {
-        if (!fastmath::step_ok(x)) break;  // env.py:117 -- the reference exit()s here; we freeze this aircraft
-        double u[4], xd[18];
-        if (LQR) {
-          lqr_action(c_lqr, x, u_in, u);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; i++) u[i] = u_in[i];
-        }
-        if (!fastmath::calc_xdot_hifi(img, x, u, xcg, xd)) break;
-#pragma unroll
-        for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);  // env.py:126
-      }
-    }
-    unsigned st = 0;
-    if (k < K) {  // stopped early: the exact status word of the frozen state
-      st = step_bounds(x, u_in);
-      if (!st) st = hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
-    }
+    int k;
+    const unsigned st = fastmath::step_aircraft<LQR>(img, x, u_in, LQR ? &c_lqr : nullptr, xcg, dt, K, k);
 #pragma unroll
     for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
     if (status) status[n] = (int)st;

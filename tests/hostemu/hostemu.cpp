@@ -86,7 +86,9 @@ __attribute__((visibility("default"))) unsigned emu_calc_xdot_fast(const double*
   double x[18], u[4], xd[18];
   for (int i = 0; i < 18; i++) x[i] = x_[i];
   for (int i = 0; i < 4; i++) u[i] = u_[i];
-  const bool ok = f16::fastmath::calc_xdot_hifi(g_fast.data(), x, u, xcg, xd);
+  double uc[4];
+  f16::fastmath::clip_commands(u, uc);
+  const bool ok = f16::fastmath::calc_xdot_hifi<false>(g_fast.data(), x, uc, xcg, xd);
   for (int i = 0; i < 18; i++) xd_[i] = ok ? xd[i] : __builtin_nan("");
   return ok ? 0u : f16::hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
 }
@@ -96,22 +98,9 @@ __attribute__((visibility("default"))) unsigned emu_step_fast(double* x_, const 
   double x[18], u_in[4];
   for (int i = 0; i < 18; i++) x[i] = x_[i];
   for (int i = 0; i < 4; i++) u_in[i] = u_[i];
-  const bool u_ok = !(f16::either_nan(u_in[0], u_in[1]) || f16::either_nan(u_in[2], u_in[3]));
   int k = 0;
-  if (u_ok)
-    for (; k < K; k++) {
-      if (!f16::fastmath::step_ok(x)) break;
-      double u[4], xd[18];
-      if (lqr) f16::lqr_action(*lqr, x, u_in, u);
-      else for (int i = 0; i < 4; i++) u[i] = u_in[i];
-      if (!f16::fastmath::calc_xdot_hifi(g_fast.data(), x, u, xcg, xd)) break;
-      for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);
-    }
-  unsigned st = 0;
-  if (k < K) {
-    st = f16::step_bounds(x, u_in);
-    if (!st) st = f16::hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
-  }
+  const unsigned st = lqr ? f16::fastmath::step_aircraft<true>(g_fast.data(), x, u_in, lqr, xcg, dt, K, k)
+                          : f16::fastmath::step_aircraft<false>(g_fast.data(), x, u_in, nullptr, xcg, dt, K, k);
   for (int i = 0; i < 18; i++) x_[i] = x[i];
   if (steps_done) *steps_done = k;
   return st;

@@ -247,3 +247,19 @@ def test_fast_step_status_words(emu_fast, oracle):
         assert s == int(st[i]) and s != 0, (i, s, int(st[i]))
         assert done.value == 0
         assert np.array_equal(x, ref[:, i], equal_nan=True)
+
+
+def test_fast_step_huge_euler_angle_takes_libm_path(emu_fast, oracle):
+    """An Euler angle beyond 2^30 rad is not a stop condition of the reference: the fast loop hands over to libm trig."""
+    from _inputs import X_TRIM_XCG25
+    from conftest import scaled_err
+    x0 = X_TRIM_XCG25.copy()
+    x0[5] = 3.0e9 + 0.25
+    x0[3] = 0.1
+    u0 = X_TRIM_XCG25[12:16].copy()
+    ref, st = oracle.step_batch(x0[:, None].copy(), u0[:, None].copy(), 200, 0.001, 1, 0.25, None, PORT)
+    x = x0.copy()
+    done = ctypes.c_int(-1)
+    assert emu_fast.emu_step_fast(_p(x), _p(u0), 200, 0.001, 0.25, None, ctypes.byref(done)) == int(st[0]) == 0
+    assert done.value == 200
+    assert scaled_err(x[:, None], ref) < 1e-10   # single aircraft: scale = |ref| per element (pure relative)
