@@ -172,7 +172,7 @@ f16::LaunchCfg cfg(bool smem_tables) {
   c.launch_counter = &G.launches;
   return c;
 }
-f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi, G.d_hifi_fast}; }
+f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi, G.d_hifi_fast, 0}; }
 f16::BatchSel sel_of(const unsigned char* fi, int fi_default, const double* xcg, double xcg_default) {
   return f16::BatchSel{fi, fi_default, xcg, xcg_default};
 }

@@ -113,21 +113,27 @@ F16_FD void sincos_quarter(double x, double& s, double& c) {
   c = fma(z, fma(z, pc, -0.5), 1.0);
 }
 
-// sin and cos for |x| < 2^30: j = rint(x 2/pi), r = x - j pi/2 in two FMAs (|j| (pi/2 - hi - mid)| < 1e-23), quadrant
-// fix-up on the sign bits; straight-line code.  Larger arguments never reach this function (angles_ok()).
-F16_FD void sincos_any(double x, double& s, double& c) {
+// sin and cos for |x| < 2^30: j = rint(x 2/pi), r = x - j pi/2 in two FMAs (|j (pi/2 - hi - mid)| < 1e-23); the quadrant
+// q = j mod 4 swaps / negates the two kernels.  Larger arguments never reach this function (step_ok()).
+F16_FD int reduce_pio2(double x, double& r) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fma(x, K.two_over_pi, magic);
   const double j = t - magic;
-  const int q = lo32(t);
-  double r = fma(-j, K.pio2_hi, x);
+  r = fma(-j, K.pio2_hi, x);
   r = fma(-j, K.pio2_mid, r);
-  double ss, cc;
-  sincos_quarter(r, ss, cc);
+  return lo32(t);
+}
+F16_FD void quadrant_fix(int q, double& s, double& c) {
   const bool sw = (q & 1) != 0;
-  const double s0 = sw ? cc : ss, c0 = sw ? ss : cc;
+  const double s0 = sw ? c : s, c0 = sw ? s : c;
   s = flip_sign(s0, (q & 2) << 30);
   c = flip_sign(c0, ((q + 1) & 2) << 30);
+}
+F16_FD void sincos_any(double x, double& s, double& c) {
+  double r;
+  const int q = reduce_pio2(x, r);
+  sincos_quarter(r, s, c);
+  quadrant_fix(q, s, c);
 }
 
 #if defined(__CUDACC__)
@@ -187,10 +193,11 @@ F16_FD int cell_of(double u, int n_cells, double& lam) {
 }
 
 // value of table `slot` of an (f, d) node at alpha weight la
-F16_FD double fd(const double* node, int slot, double la) {
-  const d2 v = ld2(node + 2 * slot);
-  return fma(la, v.y, v.x);
-}
+// Two 8-byte loads, not one 16-byte load: on B200 a warp-wide LDS.128 occupies the shared-memory pipe for 2 cycles
+// (uniform address) to 4 cycles (>= 4 distinct addresses per quarter-warp), an LDS.64 for 0.57 to 1.0
+// (tools/microbench/mb_lds.cu), i.e. half the pipe time per byte.  ptxas re-fuses adjacent 8-byte loads whenever it
+// can prove 16-byte alignment, so the kernel derives `img` from a run-time offset (DevTables::zero) it cannot see through.
+F16_FD double fd(const double* node, int slot, double la) { return fma(la, node[2 * slot + 1], node[2 * slot]); }
 F16_FD double mix(double lam, double lo, double hi) { return fma(lam, hi - lo, lo); }
 
 // |v| < 2^30 and not NaN, on the integer pipe
@@ -252,9 +259,16 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
     sincos_libm(x[3], &sphi, &cphi);
     sincos_libm(x[5], &spsi, &cpsi);
   } else {
-    sincos_any(x[4], st, ct);
-    sincos_any(x[3], sphi, cphi);
-    sincos_any(x[5], spsi, cpsi);
+    double r4, r3, r5;
+    const int q4 = reduce_pio2(x[4], r4), q3 = reduce_pio2(x[3], r3), q5 = reduce_pio2(x[5], r5);
+    sincos_quarter(r4, st, ct);
+    sincos_quarter(r3, sphi, cphi);
+    sincos_quarter(r5, spsi, cpsi);
+    if (((q4 | q3 | q5) & 3) != 0) {  // some angle outside [-pi/4, pi/4]: swap / negate per quadrant
+      quadrant_fix(q4, st, ct);
+      quadrant_fix(q3, sphi, cphi);
+      quadrant_fix(q5, spsi, cpsi);
+    }
   }
 
   double vt = x[6];
@@ -290,13 +304,10 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   double Cx_tot, Cz_tot, Cm_tot, Cy_tot, Cn_tot, Cl_tot;
   double dCz_lef;
 
-  // ---- alpha x beta group (hifi_C_lef, hifi_rudder, hifi_ailerons: hifi:1892-1926) ----
+  // ---- alpha x beta group: the delta coefficients of hifi_C_lef, hifi_rudder, hifi_ailerons (hifi:1892-1926),
+  //      tabulated at the nodes, weighted per nlplant.c:333-377 before the beta interpolation ----
   {
-    // weights of the five tables of a lateral coefficient:  C + dC_lef dlef + (dC_a20 + dC_a20_lef dlef) dail + dC_r30 drud
-    const double w_a = dail * dlef;            // C_a20_lef
-    const double w_a20 = dail - w_a;           // C_a20
-    const double w_lef = dlef - w_a;           // C_lef
-    const double w_0 = -(w_lef + w_a20 + w_a + drud);  // the dele = 0 slice subtracted by every delta
+    const double w_al = dail * dlef;  // weight of delta_C*_a20_lef
     const double* n0 = img + F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE;
     const double* n1 = n0 + F16_FI_NAC * F16_FI_G2_STRIDE;
     double dx[2], dz[2], dm[2], y[2], n[2], l[2];
@@ -305,24 +316,21 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
 #endif
     for (int k = 0; k < 2; k++) {
       const double* p = k ? n1 : n0;
-      dx[k] = fd(p, FG2_Cx_lef, la) - fd(p, FG2_Cx0, la);
-      dz[k] = fd(p, FG2_Cz_lef, la) - fd(p, FG2_Cz0, la);
-      dm[k] = fd(p, FG2_Cm_lef, la) - fd(p, FG2_Cm0, la);
-      double a = fd(p, FG2_Cy, la) * (1.0 + w_0);
-      a = fma(fd(p, FG2_Cy_lef, la), w_lef, a);
-      a = fma(fd(p, FG2_Cy_a20, la), w_a20, a);
-      a = fma(fd(p, FG2_Cy_a20_lef, la), w_a, a);
-      y[k] = fma(fd(p, FG2_Cy_r30, la), drud, a);
-      a = fd(p, FG2_Cn0, la) * w_0;
-      a = fma(fd(p, FG2_Cn_lef, la), w_lef, a);
-      a = fma(fd(p, FG2_Cn_a20, la), w_a20, a);
-      a = fma(fd(p, FG2_Cn_a20_lef, la), w_a, a);
-      n[k] = fma(fd(p, FG2_Cn_r30, la), drud, a);
-      a = fd(p, FG2_Cl0, la) * w_0;
-      a = fma(fd(p, FG2_Cl_lef, la), w_lef, a);
-      a = fma(fd(p, FG2_Cl_a20, la), w_a20, a);
-      a = fma(fd(p, FG2_Cl_a20_lef, la), w_a, a);
-      l[k] = fma(fd(p, FG2_Cl_r30, la), drud, a);
+      dx[k] = fd(p, FG2_dCx_lef, la);
+      dz[k] = fd(p, FG2_dCz_lef, la);
+      dm[k] = fd(p, FG2_dCm_lef, la);
+      double a = fma(fd(p, FG2_dCy_lef, la), dlef, fd(p, FG2_Cy, la));
+      a = fma(fd(p, FG2_dCy_a20, la), dail, a);
+      a = fma(fd(p, FG2_dCy_a20_lef, la), w_al, a);
+      y[k] = fma(fd(p, FG2_dCy_r30, la), drud, a);
+      a = fd(p, FG2_dCn_lef, la) * dlef;
+      a = fma(fd(p, FG2_dCn_a20, la), dail, a);
+      a = fma(fd(p, FG2_dCn_a20_lef, la), w_al, a);
+      n[k] = fma(fd(p, FG2_dCn_r30, la), drud, a);
+      a = fd(p, FG2_dCl_lef, la) * dlef;
+      a = fma(fd(p, FG2_dCl_a20, la), dail, a);
+      a = fma(fd(p, FG2_dCl_a20_lef, la), w_al, a);
+      l[k] = fma(fd(p, FG2_dCl_r30, la), drud, a);
     }
     dCz_lef = mix(lb, dz[0], dz[1]);
     Cx_tot = mix(lb, dx[0], dx[1]) * dlef;
@@ -398,13 +406,23 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
   const double lf_in = fma(2.0, alpha_deg, x[17]);
-  double lef_cmd = fma(lf_in, K.c1_38, K.c1_45) - atmos_out;
-  lef_cmd = clipd(lef_cmd, 0, 25);
-  xd[12] = clipd(uc[0] - x[12], -10000, 10000);
-  xd[13] = clipd(K.c20_2 * (uc[1] - x[13]), -60, 60);
-  xd[14] = clipd(K.c20_2 * (uc[2] - x[14]), -80, 80);
-  xd[15] = clipd(K.c20_2 * (uc[3] - x[15]), -120, 120);
-  xd[16] = clipd(K.inv0_136 * (lef_cmd - x[16]), -25, 25);
+  const double lef_raw = fma(lf_in, K.c1_38, K.c1_45) - atmos_out;
+  const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
+               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_raw - x[16]);
+  xd[12] = r12;
+  xd[13] = r13;
+  xd[14] = r14;
+  xd[15] = r15;
+  xd[16] = r16;
+  // rate and position limits (utils.py:297-330) only cost selects when one of them is active (or a value is NaN)
+  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (lef_raw >= 0.0) &
+        (lef_raw <= 25.0) & (fabs(r16) <= 25.0))) {
+    xd[12] = clipd(r12, -10000, 10000);
+    xd[13] = clipd(r13, -60, 60);
+    xd[14] = clipd(r14, -80, 80);
+    xd[15] = clipd(r15, -120, 120);
+    xd[16] = clipd(K.inv0_136 * (clipd(lef_raw, 0, 25) - x[16]), -25, 25);
+  }
   xd[17] = (alpha_deg - lf_in) * 7.25;
   return true;
 }

@@ -215,6 +215,9 @@ step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
     stage_tables_tma<F16_FI_BYTES>(f16_smem, img, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
     img = reinterpret_cast<const double*>(f16_smem);
   }
+#if defined(F16_FAST_LDS64)
+  img += tabs.zero;  // always 0; keeps the table gathers 8-byte loads (see fastmath::fd)
+#endif
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
     const int own = owns<1>(sel, n);
     if (own == 0) continue;

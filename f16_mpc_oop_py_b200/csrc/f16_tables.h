@@ -86,15 +86,15 @@ enum F16G2Slot {
 #define F16_FI_ETA 48        // eta_el per DH1 cell: (f, d) x 4
 #define F16_FI_POW 56        // 48 x (1/(64 c_i), 0.5*rho0*c_i^4.14), c_i = (18.5 + i)/64
 #define F16_FI_NPOW 48
-#define F16_FI_G1 152        // alpha-only group: 13 cells x 20 tables x (f, d)
-#define F16_FI_G1_STRIDE 40
-#define F16_FI_G3B 672       // (Cn, Cl) on DH2 x beta x alpha-cell: 3*19*13 nodes x 2 x (f, d)
+#define F16_FI_G1 152        // alpha-only group: 13 cells x 20 tables x (f, d) (+2 pad: cell stride 336 B = 80 mod 128)
+#define F16_FI_G1_STRIDE 42
+#define F16_FI_G3B 698       // (Cn, Cl) on DH2 x beta x alpha-cell: 3*19*13 nodes x 2 x (f, d)
 #define F16_FI_G3B_STRIDE 4
-#define F16_FI_G3A 3636      // (Cx, Cz, Cm) on DH1 x beta x alpha-cell: 5*19*13 nodes x 3 x (f, d)
+#define F16_FI_G3A 3662      // (Cx, Cz, Cm) on DH1 x beta x alpha-cell: 5*19*13 nodes x 3 x (f, d)
 #define F16_FI_G3A_STRIDE 6
-#define F16_FI_G2 11046      // alpha x beta group: 19*13 nodes x 21 tables x (f, d)
-#define F16_FI_G2_STRIDE 42
-#define F16_FI_DOUBLES 21420
+#define F16_FI_G2 11072      // alpha x beta group: 19*13 nodes x 16 tables x (f, d) (+2 pad: node stride 272 B = 16 mod 128,
+#define F16_FI_G2_STRIDE 34    //   so that lanes in neighbouring cells do not meet in the same shared-memory banks)
+#define F16_FI_DOUBLES 19470
 #define F16_FI_BYTES (F16_FI_DOUBLES * 8)
 
 enum F16FastG1 {  // table order inside a G1 cell
@@ -102,11 +102,11 @@ enum F16FastG1 {  // table order inside a G1 cell
   FG1_Cnr, FG1_dCnr_lef, FG1_Cnp, FG1_dCnp_lef, FG1_dCnbeta, FG1_Clr, FG1_dClr_lef, FG1_Clp, FG1_dClp_lef, FG1_dClbeta,
   FG1_COUNT
 };
-enum F16FastG2 {  // table order inside a G2 node
-  FG2_Cx0 = 0, FG2_Cx_lef, FG2_Cz0, FG2_Cz_lef, FG2_Cm0, FG2_Cm_lef,
-  FG2_Cy, FG2_Cy_lef, FG2_Cy_a20, FG2_Cy_a20_lef, FG2_Cy_r30,
-  FG2_Cn0, FG2_Cn_lef, FG2_Cn_a20, FG2_Cn_a20_lef, FG2_Cn_r30,
-  FG2_Cl0, FG2_Cl_lef, FG2_Cl_a20, FG2_Cl_a20_lef, FG2_Cl_r30,
+enum F16FastG2 {  // table order inside a G2 node: the delta coefficients of hifi_C_lef / hifi_rudder / hifi_ailerons
+  FG2_dCx_lef = 0, FG2_dCz_lef, FG2_dCm_lef,                       // C_lef(a,b) - C(a,b,0)            hifi:1892-1899
+  FG2_Cy, FG2_dCy_lef, FG2_dCy_a20, FG2_dCy_a20_lef, FG2_dCy_r30,  // Cy; C_a20 - C; C_a20_lef - C_lef - (C_a20 - C); C_r30 - C
+  FG2_dCn_lef, FG2_dCn_a20, FG2_dCn_a20_lef, FG2_dCn_r30,          //                                   hifi:1913-1926
+  FG2_dCl_lef, FG2_dCl_a20, FG2_dCl_a20_lef, FG2_dCl_r30,
   FG2_COUNT
 };
 

@@ -318,16 +318,36 @@ void build_hifi_fast_image(const std::vector<double>& p, bool clr_from_file, std
         put(n + 2, FT_Cz, 20, ia, ib, id);
         put(n + 4, FT_Cm, 20, ia, ib, id);
       }
-  // alpha x beta group; dele = 0 is breakpoint 2 of DH1 and breakpoint 1 of DH2
-  const int g2_src[FG2_COUNT][3] = {
-      {FT_Cx, 20, 2}, {FT_Cx_lef, 14, 0}, {FT_Cz, 20, 2}, {FT_Cz_lef, 14, 0}, {FT_Cm, 20, 2}, {FT_Cm_lef, 14, 0},
-      {FT_Cy, 20, 0}, {FT_Cy_lef, 14, 0}, {FT_Cy_a20, 20, 0}, {FT_Cy_a20_lef, 14, 0}, {FT_Cy_r30, 20, 0},
-      {FT_Cn, 20, 1}, {FT_Cn_lef, 14, 0}, {FT_Cn_a20, 20, 0}, {FT_Cn_a20_lef, 14, 0}, {FT_Cn_r30, 20, 0},
-      {FT_Cl, 20, 1}, {FT_Cl_lef, 14, 0}, {FT_Cl_a20, 20, 0}, {FT_Cl_a20_lef, 14, 0}, {FT_Cl_r30, 20, 0}};
+  // alpha x beta group: node values of the reference's delta coefficients (interpolation is linear, so the delta of
+  // the interpolants is the interpolant of the node deltas); dele = 0 is breakpoint 2 of DH1 and breakpoint 1 of DH2
+  auto node_val = [&](int slot, int ia, int ib) {
+    auto A20 = [&](int base, int a20, int base_d) { return at(a20, 20, ia, ib, 0) - at(base, 20, ia, ib, base_d); };
+    switch (slot) {
+      case FG2_dCx_lef: return at(FT_Cx_lef, 14, ia, ib, 0) - at(FT_Cx, 20, ia, ib, 2);
+      case FG2_dCz_lef: return at(FT_Cz_lef, 14, ia, ib, 0) - at(FT_Cz, 20, ia, ib, 2);
+      case FG2_dCm_lef: return at(FT_Cm_lef, 14, ia, ib, 0) - at(FT_Cm, 20, ia, ib, 2);
+      case FG2_Cy: return at(FT_Cy, 20, ia, ib, 0);
+      case FG2_dCy_lef: return at(FT_Cy_lef, 14, ia, ib, 0) - at(FT_Cy, 20, ia, ib, 0);
+      case FG2_dCy_a20: return A20(FT_Cy, FT_Cy_a20, 0);
+      case FG2_dCy_a20_lef: return at(FT_Cy_a20_lef, 14, ia, ib, 0) - at(FT_Cy_lef, 14, ia, ib, 0) - A20(FT_Cy, FT_Cy_a20, 0);
+      case FG2_dCy_r30: return at(FT_Cy_r30, 20, ia, ib, 0) - at(FT_Cy, 20, ia, ib, 0);
+      case FG2_dCn_lef: return at(FT_Cn_lef, 14, ia, ib, 0) - at(FT_Cn, 20, ia, ib, 1);
+      case FG2_dCn_a20: return A20(FT_Cn, FT_Cn_a20, 1);
+      case FG2_dCn_a20_lef: return at(FT_Cn_a20_lef, 14, ia, ib, 0) - at(FT_Cn_lef, 14, ia, ib, 0) - A20(FT_Cn, FT_Cn_a20, 1);
+      case FG2_dCn_r30: return at(FT_Cn_r30, 20, ia, ib, 0) - at(FT_Cn, 20, ia, ib, 1);
+      case FG2_dCl_lef: return at(FT_Cl_lef, 14, ia, ib, 0) - at(FT_Cl, 20, ia, ib, 1);
+      case FG2_dCl_a20: return A20(FT_Cl, FT_Cl_a20, 1);
+      case FG2_dCl_a20_lef: return at(FT_Cl_a20_lef, 14, ia, ib, 0) - at(FT_Cl_lef, 14, ia, ib, 0) - A20(FT_Cl, FT_Cl_a20, 1);
+      default: return at(FT_Cl_r30, 20, ia, ib, 0) - at(FT_Cl, 20, ia, ib, 1);  // FG2_dCl_r30
+    }
+  };
   for (int ib = 0; ib < F16_N_B; ib++)
     for (int ia = 0; ia < F16_FI_NAC; ia++)
-      for (int s = 0; s < FG2_COUNT; s++)
-        put(&img[F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE + 2 * s], g2_src[s][0], g2_src[s][1], ia, ib, g2_src[s][2]);
+      for (int s = 0; s < FG2_COUNT; s++) {
+        double* dst = &img[F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE + 2 * s];
+        dst[0] = node_val(s, ia, ib);
+        dst[1] = node_val(s, ia + 1, ib) - dst[0];
+      }
 }
 
 static const double LOFI_DATA[F16_IMG_LOFI_DOUBLES] = {
