@@ -307,7 +307,7 @@ def run_ours(args):
                 "workload": ("cfg5: closed-loop LQR Monte Carlo, hifi xcg 0.35" if law is not None else
                              "cfg2: 2^20-aircraft hifi batch, +-5% about trim, 10000 fused Euler steps, xcg 0.25"),
                 "aircraft_per_gpu": n, "euler_steps_per_step": ke, "dt": args.dt, "xcg": xcg, "math": args.math,
-                "step_threads": args.step_threads or 512, "table_staging": "tma_smem" if not args.no_table_staging else "l2",
+                "step_threads": args.step_threads or 384, "table_staging": "tma_smem" if not args.no_table_staging else "l2",
                 "cold_inputs": "state re-copied from a 144 MB pristine buffer (> L2) before every launch",
                 "alive_fraction": alive,
             },

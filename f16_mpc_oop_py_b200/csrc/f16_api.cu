@@ -52,7 +52,7 @@ struct State {
   int math_mode = F16_MATH_STRICT;
   int clr_mode = F16_CLR_AS_BUILT;
   bool smem_tables = true;
-  int step_threads = 512;
+  int step_threads = 384;
   double default_xcg = 0.25;
   int last_status = 0;
   unsigned long long launches = 0;

@@ -100,7 +100,7 @@ int f16_set_clr_mode(int mode);       /* F16_CLR_*; rebuilds the device tables; 
 void f16_set_default_xcg(double xcg); /* for the legacy Nlplant symbol; default 0.25 or $F16_XCG */
 int f16_set_table_staging(int mode);  /* 1 (default): tables staged in shared memory by TMA bulk copy;
                                          0: read through L1/L2 with ld.global.nc (for A/B measurements) */
-int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256, 384, 512 (default), 640, 768 or 1024 */
+int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256, 384 (default), 512, 640, 768 or 1024 */
 /* sha256 (hex, 64 chars + NUL) of the canonical table payload in use */
 int f16_tables_sha256(char *out65);
 

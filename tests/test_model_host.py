@@ -263,3 +263,28 @@ def test_fast_step_huge_euler_angle_takes_libm_path(emu_fast, oracle):
     assert emu_fast.emu_step_fast(_p(x), _p(u0), 200, 0.001, 0.25, None, ctypes.byref(done)) == int(st[0]) == 0
     assert done.value == 200
     assert scaled_err(x[:, None], ref) < 1e-10   # single aircraft: scale = |ref| per element (pure relative)
+
+
+def test_fast_step_on_the_actuator_limits(emu_fast, oracle):
+    """Actuator states that start ON their limits with commands beyond them (the saturated branches of the fast
+    arithmetic): status and state must follow the oracle."""
+    from _inputs import X_TRIM_XCG25
+    from conftest import scaled_err
+    cases = []
+    for (T, dh, da, dr, lf2), u in (((19000.0, 25.0, 21.5, 30.0, 25.0), (25000.0, 40.0, 30.0, 45.0)),
+                                     ((1000.0, -25.0, -21.5, -30.0, 0.0), (0.0, -40.0, -30.0, -45.0)),
+                                     ((19000.0, -25.0, 21.5, -30.0, 0.0), (500.0, 30.0, -30.0, 31.0)),
+                                     ((18999.999999999996, 24.999999999999996, 0.0, 0.0, 1e-300), (19000.0, 25.0, 21.5, 30.0))):
+        x = X_TRIM_XCG25.copy()
+        x[12:17] = [T, dh, da, dr, lf2]
+        cases.append((x, np.array(u)))
+    for x0, u0 in cases:
+        ref, st = oracle.step_batch(x0[:, None].copy(), u0[:, None].copy(), 1500, 0.001, 1, 0.25, None, PORT)
+        x = x0.copy()
+        done = ctypes.c_int(-1)
+        s = emu_fast.emu_step_fast(_p(x), _p(u0.copy()), 1500, 0.001, 0.25, None, ctypes.byref(done))
+        assert s == int(st[0])
+        # a frozen aircraft stops at the same step unless the violated threshold is crossed within rounding
+        assert scaled_err(x[:, None], ref) < 1e-7 if s else scaled_err(x[:, None], ref) < 1e-9
+        assert np.all(x[12] >= 1000) and np.all(x[12] <= 19000) and abs(x[13]) <= 25 and abs(x[14]) <= 21.5 and abs(x[15]) <= 30
+        assert 0 <= x[16] <= 25
