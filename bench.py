@@ -166,6 +166,38 @@ def run_reference(args):
     return 0
 
 
+def measure_jacobians(L, ck, n, x_trim, u_trim, xcg, seed, scheme, reps=3):
+    """Jacobians/s of linearise_batch_dev (A [18x18] + B [18x4] per trim point, env.py:294-342) on resident inputs:
+    n perturbed-trim points, `reps` timed launches after one warm-up.  scheme 0 = forward (23 columns), 1 = central (44)."""
+    x, u = perturbed_trim(n, x_trim, u_trim, seed, frac=0.02)
+    d_x, d_u = L.f16_dev_alloc(x.nbytes), L.f16_dev_alloc(u.nbytes)
+    d_A, d_B, d_st = L.f16_dev_alloc(n * 324 * 8), L.f16_dev_alloc(n * 72 * 8), L.f16_dev_alloc(4 * n)
+    if not (d_x and d_u and d_A and d_B and d_st):
+        raise RuntimeError("device allocation failed: " + L.f16_last_error().decode())
+    ck(L.f16_memcpy_h2d(d_x, x.ctypes.data, x.nbytes), "h2d")
+    ck(L.f16_memcpy_h2d(d_u, u.ctypes.data, u.nbytes), "h2d")
+
+    def launch():
+        ck(L.linearise_batch_dev(d_x, n, d_u, n, n, 1e-5, scheme, d_A, d_B, None, 1, None, xcg, d_st), "linearise_batch_dev")
+
+    launch()
+    ck(L.f16_sync(), "sync")
+    ck(L.f16_timer_start(), "timer")
+    for _ in range(reps):
+        launch()
+    ms = ctypes.c_float(0.0)
+    ck(L.f16_timer_stop(ctypes.byref(ms)), "timer")
+    st = np.zeros(n, dtype=np.int32)
+    ck(L.f16_memcpy_d2h(st.ctypes.data, d_st, st.nbytes), "d2h")
+    for p in (d_x, d_u, d_A, d_B, d_st):
+        L.f16_dev_free(p)
+    per_launch_ms = float(ms.value) / reps
+    return {"value": n / (per_launch_ms * 1e-3), "unit": "Jacobian pairs (A 18x18, B 18x4)/s", "points": n,
+            "scheme": "central" if scheme else "forward", "eps": 1e-5, "ms_per_launch": per_launch_ms,
+            "valid_fraction": float((st == 0).mean()),
+            "flop_per_jacobian": 32300.0 if scheme else 17200.0, "out_bytes_per_jacobian": 396 * 8}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -272,6 +304,11 @@ def run_ours(args):
     for p in (hx, hu, hs):
         L.f16_host_free_pinned(p)
 
+    jac = None
+    if not args.no_jacobians:
+        jac = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 1)
+        jac_fwd = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 0)
+
     # max over ranks (timings are the slowest rank's); the only collective: end-of-run statistics
     from f16_mpc_oop_py_b200 import shard
     dev = f"cuda:{local}" if dist else "cpu"
@@ -326,6 +363,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if jac:   # second half of BASELINE.json's metric; per-GPU figures of rank 0 (ranks run identical, independent work)
+            peak_tf = float(peak.value)
+            for j in (jac, jac_fwd):
+                j["fp64_frac"] = j["value"] * j["flop_per_jacobian"] / 1e12 / peak_tf if peak_tf else None
+                j["value_all_gpus"] = j["value"] * world
+            line["jacobians"] = {"central": jac, "forward": jac_fwd}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -351,6 +394,8 @@ def main():
     ap.add_argument("--no-table-staging", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-jacobians", action="store_true", help="skip the linearise_batch (Jacobians/s) measurement")
+    ap.add_argument("--jac-points", type=int, default=1 << 17, help="trim points per GPU in the Jacobian measurement")
     ap.add_argument("--ref-aircraft", type=int, default=4096, help="aircraft in the CPU sample")
     ap.add_argument("--ref-euler-steps", type=int, default=200, help="Euler steps in the CPU sample")
     args = ap.parse_args()

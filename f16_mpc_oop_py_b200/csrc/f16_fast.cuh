@@ -406,22 +406,22 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
   const double lf_in = fma(2.0, alpha_deg, x[17]);
-  const double lef_raw = fma(lf_in, K.c1_38, K.c1_45) - atmos_out;
+  // flap command saturation (utils.py:297): active in ordinary flight (the trim flap angle is 0.4 deg), so a select
+  const double lef_cmd = clipd(fma(lf_in, K.c1_38, K.c1_45) - atmos_out, 0, 25);
   const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
-               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_raw - x[16]);
+               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_cmd - x[16]);
   xd[12] = r12;
   xd[13] = r13;
   xd[14] = r14;
   xd[15] = r15;
   xd[16] = r16;
-  // rate and position limits (utils.py:297-330) only cost selects when one of them is active (or a value is NaN)
-  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (lef_raw >= 0.0) &
-        (lef_raw <= 25.0) & (fabs(r16) <= 25.0))) {
+  // rate limits (utils.py:299-330) only cost selects when one of them is active (or a value is NaN)
+  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
     xd[12] = clipd(r12, -10000, 10000);
     xd[13] = clipd(r13, -60, 60);
     xd[14] = clipd(r14, -80, 80);
     xd[15] = clipd(r15, -120, 120);
-    xd[16] = clipd(K.inv0_136 * (clipd(lef_raw, 0, 25) - x[16]), -25, 25);
+    xd[16] = clipd(r16, -25, 25);
   }
   xd[17] = (alpha_deg - lf_in) * 7.25;
   return true;
