@@ -290,12 +290,16 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
 
   // navigation + kinematics, nlplant.c:148-176
   const double U = vc * ca, V = vt * sb, W = vc * sa;
-  xd[0] = U * (ct * cpsi) + V * (sphi * cpsi * st - cphi * spsi) + W * (cphi * st * cpsi + sphi * spsi);
-  xd[1] = U * (ct * spsi) + V * (sphi * spsi * st + cphi * cpsi) + W * (cphi * st * spsi - sphi * cpsi);
-  xd[2] = U * st - V * (sphi * ct) - W * (cphi * ct);
-  const double qr = Q * sphi + R * cphi;
+  {
+    const double sphi_cpsi = sphi * cpsi, cphi_spsi = cphi * spsi, sphi_spsi = sphi * spsi, cphi_cpsi = cphi * cpsi,
+                 cphi_st = cphi * st;
+    xd[0] = fma(U, ct * cpsi, fma(V, fma(sphi_cpsi, st, -cphi_spsi), W * fma(cphi_st, cpsi, sphi_spsi)));
+    xd[1] = fma(U, ct * spsi, fma(V, fma(sphi_spsi, st, cphi_cpsi), W * fma(cphi_st, spsi, -sphi_cpsi)));
+    xd[2] = fma(U, st, -fma(V, sphi * ct, W * (cphi * ct)));
+  }
+  const double qr = fma(Q, sphi, R * cphi);
   xd[3] = fma(st * inv_ct, qr, P);
-  xd[4] = Q * cphi - R * sphi;
+  xd[4] = fma(Q, cphi, -(R * sphi));
   xd[5] = qr * inv_ct;
 
   // weights of the damping terms, nlplant.c:333-377
@@ -385,13 +389,13 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   // body-axis accelerations, nlplant.c:383-387
   const double qS_m = qbar * K.S_m;
   const double gct = K.g * ct;
-  const double Udot = fma(T, K.inv_m, fma(qS_m, Cx_tot, fma(-K.g, st, R * V - Q * W)));
-  const double Vdot = fma(qS_m, Cy_tot, fma(gct, sphi, P * W - R * U));
-  const double Wdot = fma(qS_m, Cz_tot, fma(gct, cphi, Q * U - P * V));
+  const double Udot = fma(T, K.inv_m, fma(qS_m, Cx_tot, fma(-K.g, st, fma(R, V, -(Q * W)))));
+  const double Vdot = fma(qS_m, Cy_tot, fma(gct, sphi, fma(P, W, -(R * U))));
+  const double Wdot = fma(qS_m, Cz_tot, fma(gct, cphi, fma(Q, U, -(P * V))));
   // nlplant.c:393-405 with U = vt ca cb, V = vt sb, W = vt sa cb substituted (vt cancels)
-  const double vtd = fma(ca * cb, Udot, fma(sb, Vdot, sa * cb * Wdot));
+  const double vtd = fma(ca * cb, Udot, fma(sb, Vdot, (sa * cb) * Wdot));
   xd[6] = vtd;
-  xd[7] = (ca * Wdot - sa * Udot) * inv_vc;
+  xd[7] = fma(ca, Wdot, -(sa * Udot)) * inv_vc;
   xd[8] = fma(-sb, vtd, Vdot) * inv_vc;
 
   // moments, nlplant.c:413-436 (Heng = 0), inertia ratios folded into constants
@@ -399,7 +403,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   const double L_tot = Cl_tot * qSb, N_tot = Cn_tot * qSb, M_tot = Cm_tot * (qbar * (S * cbar));
   const double PQ = P * Q, QR = Q * R;
   xd[9] = fma(K.ixx_l, L_tot, fma(K.ixx_n, N_tot, fma(K.ixx_qr, QR, K.ixx_pq * PQ)));
-  xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * (P * P - R * R)));
+  xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * fma(P, P, -(R * R))));
   xd[11] = fma(K.izz_n, N_tot, fma(K.izz_l, L_tot, fma(K.izz_pq, PQ, K.izz_qr * QR)));
 
   // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)

@@ -10,9 +10,7 @@
 #include <stdint.h>
 
 #include "f16_kernels.cuh"
-#if defined(F16_FAST)
-#include "f16_fast.cuh"
-#endif
+#include "f16_kernels_common.cuh"
 
 #ifndef F16_NS
 #error "compile with -DF16_NS=strict or -DF16_NS=fast"
@@ -26,53 +24,12 @@
 namespace f16 {
 namespace F16_NS {
 
-// ------------------------------------------------------------------------------------------------------
-// table staging: global -> shared with TMA bulk copies completing on one mbarrier
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int BYTES>
-__device__ __forceinline__ void stage_tables_tma(void* dst, const void* src, unsigned long long* bar) {
-  static_assert(BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
-  const uint32_t bar_a = smem_u32(bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
-    constexpr int CHUNK = 32768;
-#pragma unroll 1
-    for (int off = 0; off < BYTES; off += CHUNK) {
-      const int n = (BYTES - off) < CHUNK ? (BYTES - off) : CHUNK;
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(static_cast<char*>(dst) + off)),
-          "l"(static_cast<const char*>(src) + off), "r"(n), "r"(bar_a)
-          : "memory");
-    }
-  }
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar_a), "r"(0)
-        : "memory");
-  }
-}
-
 template <int FI>
 struct Img {
   static constexpr int DOUBLES = FI ? F16_IMG_HIFI_DOUBLES : F16_IMG_LOFI_DOUBLES;
   static constexpr int BYTES = DOUBLES * 8;
   static constexpr int SMEM_BYTES = BYTES + 16;  // + the mbarrier
 };
-
-extern __shared__ __align__(128) unsigned char f16_smem[];
 
 template <int FI, bool SMEM>
 __device__ __forceinline__ const double* acquire_tables(const DevTables& t) {
@@ -81,17 +38,6 @@ __device__ __forceinline__ const double* acquire_tables(const DevTables& t) {
   stage_tables_tma<Img<FI>::BYTES>(f16_smem, g, reinterpret_cast<unsigned long long*>(f16_smem + Img<FI>::BYTES));
   return reinterpret_cast<const double*>(f16_smem);
 }
-
-// which aircraft does the FI instantiation own?  (per-aircraft flags other than 0/1 are reported by FI == 1)
-template <int FI>
-__device__ __forceinline__ int owns(const BatchSel& s, long long n) {
-  const int f = s.fi ? (int)s.fi[n] : s.fi_default;
-  if (f == FI) return 1;
-  if (FI == 1 && f != 0) return -1;
-  return 0;
-}
-
-__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // ------------------------------------------------------------------------------------------------------
 // Nlplant_batch: xu [17][N] -> xdot [18][N]
@@ -196,51 +142,6 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
     if (steps_done) steps_done[n] = k;
   }
 }
-
-#if defined(F16_FAST)
-// ------------------------------------------------------------------------------------------------------
-// step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
-// (fast table image: 171 KB in shared memory, one CTA per SM).  The per-step checks are the cheap "all inside"
-// form; the exact status word is rebuilt from the frozen state when an aircraft stops.
-// ------------------------------------------------------------------------------------------------------
-constexpr int FAST_SMEM_BYTES = F16_FI_BYTES + 16;
-
-template <bool SMEM, bool LQR, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
-                      const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
-                      int* __restrict__ status, int* __restrict__ steps_done) {
-  const double* img = tabs.hifi_fast;
-  if (SMEM) {
-    stage_tables_tma<F16_FI_BYTES>(f16_smem, img, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
-    img = reinterpret_cast<const double*>(f16_smem);
-  }
-#if defined(F16_FAST_LDS64)
-  img += tabs.zero;  // always 0; keeps the table gathers 8-byte loads (see fastmath::fd)
-#endif
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
-    const int own = owns<1>(sel, n);
-    if (own == 0) continue;
-    if (own < 0) {
-      if (status) status[n] = (int)ST_FIDELITY;
-      if (steps_done) steps_done[n] = 0;
-      continue;
-    }
-    double x[18], u_in[4];
-#pragma unroll
-    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
-#pragma unroll
-    for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
-    const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
-    int k;
-    const unsigned st = fastmath::step_aircraft<LQR>(img, x, u_in, LQR ? &c_lqr : nullptr, xcg, dt, K, k);
-#pragma unroll
-    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
-    if (status) status[n] = (int)st;
-    if (steps_done) steps_done[n] = k;
-  }
-}
-#endif  // F16_FAST
 
 // ------------------------------------------------------------------------------------------------------
 // linearise_batch: finite-difference A [18x18], B [18x4] of _calc_xdot (env.py:294-342).
@@ -413,41 +314,7 @@ atmos_kernel(const double* __restrict__ alt, const double* __restrict__ vt, long
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
-static int grid_for(long long work_items, int per_block, int resident) {
-  long long b = (work_items + per_block - 1) / per_block;
-  if (b < 1) b = 1;
-  if (b > resident) b = resident;
-  return (int)b;
-}
-
-template <typename Kern>
-static cudaError_t prepare(Kern kern, int threads, int smem, int sm_count, int* resident) {
-  cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-  }
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  *resident = per_sm * sm_count;
-  return cudaSuccess;
-}
-
 static bool wants(const BatchSel& s, int FI) { return s.fi != nullptr || s.fi_default == FI || (FI == 1 && s.fi_default != 0); }
-
-// persistent launch: grid = min(ceil(items / per_block), resident CTAs)
-template <typename Kern, typename... Args>
-static cudaError_t launch_persistent(const LaunchCfg& cfg, Kern kern, int threads, int smem, long long items,
-                                     int per_block, Args... args) {
-  int resident = 0;
-  cudaError_t e = prepare(kern, threads, smem, cfg.sm_count, &resident);
-  if (e != cudaSuccess) return e;
-  kern<<<grid_for(items, per_block, resident), threads, smem, cfg.stream>>>(args...);
-  if (cfg.launch_counter) ++*cfg.launch_counter;
-  return cudaGetLastError();
-}
 
 template <int FI>
 static int table_smem(bool smem_tables) { return smem_tables ? Img<FI>::SMEM_BYTES : 0; }
@@ -484,19 +351,6 @@ cudaError_t launch_calc_xdot(const LaunchCfg& cfg, const DevTables& tabs, const 
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*);
 
-#if defined(F16_FAST)
-template <bool LQR>
-static StepKern pick_step_hifi_fast(bool smem_tables, int& threads) {
-  if (!smem_tables) { threads = 256; return step_hifi_fast_kernel<false, LQR, 256>; }
-  if (threads <= 256) { threads = 256; return step_hifi_fast_kernel<true, LQR, 256>; }
-  if (threads <= 384) { threads = 384; return step_hifi_fast_kernel<true, LQR, 384>; }
-  if (threads <= 512) { threads = 512; return step_hifi_fast_kernel<true, LQR, 512>; }
-  if (threads <= 640) { threads = 640; return step_hifi_fast_kernel<true, LQR, 640>; }
-  threads = 768;
-  return step_hifi_fast_kernel<true, LQR, 768>;
-}
-#endif
-
 template <int FI, bool LQR>
 static StepKern pick_step(bool smem_tables, int& threads) {
   if (!smem_tables) { threads = 256; return step_kernel<FI, false, LQR, 256>; }
@@ -522,14 +376,14 @@ cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const Batch
     if (!wants(sel, FI)) continue;
     int threads = cfg.step_threads;
 #if defined(F16_FAST)
-    StepKern k = FI ? (lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads))
-                    : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
-    const int smem = FI ? (cfg.smem_tables ? FAST_SMEM_BYTES : 0) : table_smem<0>(cfg.smem_tables);
-#else
+    if (FI == 1) {  // the hifi step of F16_MATH_FAST lives in f16_step_fast.cu (explicit FMAs, -fmad=false)
+      e = launch_step_hifi_fast(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, status, steps_done);
+      continue;
+    }
+#endif
     StepKern k = FI ? (lqr_host ? pick_step<1, true>(cfg.smem_tables, threads) : pick_step<1, false>(cfg.smem_tables, threads))
                     : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
     const int smem = FI ? table_smem<1>(cfg.smem_tables) : table_smem<0>(cfg.smem_tables);
-#endif
     e = launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
   }
   return e;

@@ -52,6 +52,10 @@ F16_DECLARE_LAUNCHERS
 }
 namespace fast {
 F16_DECLARE_LAUNCHERS
+// f16_step_fast.cu: the hifi step on the arithmetic of f16_fast.cuh
+cudaError_t launch_step_hifi_fast(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,
+                                  const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
+                                  int* status, int* steps_done);
 }
 
 // FP64 FMA micro-benchmark (f16_peak.cu): returns flops executed

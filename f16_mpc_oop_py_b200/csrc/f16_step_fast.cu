@@ -1,0 +1,85 @@
+// f16_step_fast.cu -- the hifi fused Euler step of F16_MATH_FAST (f16_fast.cuh).
+// Compiled with -fmad=false: every fused multiply-add in this kernel is an explicit fma() in the source, so the
+// result does not depend on which mul/add pairs ptxas would have chosen to contract in a given instantiation
+// (CTA size, table staging) -- all variants of the kernel, and the host emulation of the tests, agree bit for bit.
+#include "f16_kernels_common.cuh"
+#include "f16_fast.cuh"
+
+namespace f16 {
+namespace fast {
+
+__constant__ LqrLaw c_lqr_fast;
+
+// ------------------------------------------------------------------------------------------------------
+// step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
+// (fast table image: 171 KB in shared memory, one CTA per SM).  The per-step checks are the cheap "all inside"
+// form; the exact status word is rebuilt from the frozen state when an aircraft stops.
+// ------------------------------------------------------------------------------------------------------
+constexpr int FAST_SMEM_BYTES = F16_FI_BYTES + 16;
+
+template <bool SMEM, bool LQR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
+                      const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
+                      int* __restrict__ status, int* __restrict__ steps_done) {
+  const double* img = tabs.hifi_fast;
+  if (SMEM) {
+    stage_tables_tma<F16_FI_BYTES>(f16_smem, img, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
+    img = reinterpret_cast<const double*>(f16_smem);
+  }
+#if defined(F16_FAST_LDS64)
+  img += tabs.zero;  // always 0; keeps the table gathers 8-byte loads (see fastmath::fd)
+#endif
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<1>(sel, n);
+    if (own == 0) continue;
+    if (own < 0) {
+      if (status) status[n] = (int)ST_FIDELITY;
+      if (steps_done) steps_done[n] = 0;
+      continue;
+    }
+    double x[18], u_in[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
+    const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+    int k;
+    const unsigned st = fastmath::step_aircraft<LQR>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (status) status[n] = (int)st;
+    if (steps_done) steps_done[n] = k;
+  }
+}
+
+using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
+                          int*);
+
+template <bool LQR>
+static StepKern pick_step_hifi_fast(bool smem_tables, int& threads) {
+  if (!smem_tables) { threads = 256; return step_hifi_fast_kernel<false, LQR, 256>; }
+  if (threads <= 256) { threads = 256; return step_hifi_fast_kernel<true, LQR, 256>; }
+  if (threads <= 384) { threads = 384; return step_hifi_fast_kernel<true, LQR, 384>; }
+  if (threads <= 512) { threads = 512; return step_hifi_fast_kernel<true, LQR, 512>; }
+  if (threads <= 640) { threads = 640; return step_hifi_fast_kernel<true, LQR, 640>; }
+  threads = 768;
+  return step_hifi_fast_kernel<true, LQR, 768>;
+}
+
+cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x,
+                                  const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
+                                  int* status, int* steps_done) {
+  if (N <= 0) return cudaSuccess;
+  if (lqr_host) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_lqr_fast, lqr_host, sizeof(LqrLaw), 0, cudaMemcpyHostToDevice, cfg.stream);
+    if (e != cudaSuccess) return e;
+  }
+  int threads = cfg.step_threads;
+  StepKern k = lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads);
+  const int smem = cfg.smem_tables ? FAST_SMEM_BYTES : 0;
+  return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+}
+
+}  // namespace fast
+}  // namespace f16
