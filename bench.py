@@ -126,6 +126,7 @@ def cpu_reference_rate(aircraft, euler_steps, seed, repeats=1, lqr=None):
     """aircraft-steps/s of the reference Nlplant/atmos under the restated env.py step, OpenMP over aircraft."""
     from oracle import PORT, REF, get_oracle
     o = get_oracle()
+    o.set_threads(len(os.sched_getaffinity(0)))   # all host cores of this process, whatever OMP_NUM_THREADS says
     kind, be = ("reference", REF) if o.open_ref() else ("port", PORT)
     x_trim, u_trim, _ = trim_state("xcg25")
     x, u = perturbed_trim(aircraft, x_trim, u_trim, seed)
@@ -219,10 +220,9 @@ def run_ours(args):
     x, u = perturbed_trim(n, x_trim, u_trim, seed=rank_seed(0xF16, rank))
     law = None
     if args.workload == "lqr":
-        K = np.zeros((3, 9))
-        K[0, [2, 5]] = [-30.0, -8.0]
-        K[1, [0, 4]] = [-3.0, -1.5]
-        K[2, [3, 6]] = [2.0, -1.0]
+        # BASELINE cfg 5: u = u0 - K (x - x_trim) on the reference's MPC states / inputs with the reference's own gain
+        # (tests/golden: K_lqr = F16._calc_LQR_gain() = -dlqr(...), env.py:344-358, so the regulator gain is -K_lqr)
+        K = -np.load(os.path.join(GOLDEN, f"env_{tag}.npz"))["K_lqr"]
         law = f16.make_lqr(K, mpc_idx, x_trim[mpc_idx], u_trim, rows=[1, 2, 3])
     law_p = ctypes.byref(law) if law is not None else None
 

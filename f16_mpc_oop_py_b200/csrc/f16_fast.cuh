@@ -221,6 +221,58 @@ F16_FD bool step_ok(const double (&x)[18]) {
   return ok;
 }
 
+// The closed-loop law of f16_lqr_t scattered to state order by the host (make_dense_law): every selected state is a
+// compile-time register here, columns that carry no gain are skipped by warp-uniform branches on `colmask`.
+//     u[r] = u0[r] - extra[r] - sum_i Kf[i][r] (x[i] - xr[i])        for rows in row_mask
+struct LqrDense {
+  int colmask, row_mask;
+  double Kf[18][4];
+  double xr[18];
+  double u0[4];     // u0[r] - extra[r]; extra collects the constant left by states selected more than once
+};
+
+#if defined(__CUDACC__)
+__host__
+#endif
+static inline void make_dense_law(const LqrLaw& l, LqrDense& d) {
+  d = LqrDense();
+  d.row_mask = l.row_mask;
+  for (int r = 0; r < 4; r++) d.u0[r] = l.u0[r];
+  for (int j = 0; j < l.n_sel; j++) {
+    const int i = l.sel[j];
+    if (!((d.colmask >> i) & 1)) {
+      d.colmask |= 1 << i;
+      d.xr[i] = l.x_ref[j];
+      for (int r = 0; r < 4; r++) d.Kf[i][r] = l.K[r][j];
+    } else {  // K2 (x - r2) = K2 (x - r1) + K2 (r1 - r2)
+      for (int r = 0; r < 4; r++) {
+        d.Kf[i][r] += l.K[r][j];
+        d.u0[r] -= l.K[r][j] * (d.xr[i] - l.x_ref[j]);
+      }
+    }
+  }
+}
+
+F16_FD void lqr_action_dense(const LqrDense& l, const double (&x)[18], const double (&u_in)[4], double (&u)[4]) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 18; i++) {
+    if ((l.colmask >> i) & 1) {
+      const double e = x[i] - l.xr[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int r = 0; r < 4; r++) acc[r] = fma(l.Kf[i][r], e, acc[r]);
+    }
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 4; r++) u[r] = ((l.row_mask >> r) & 1) ? (l.u0[r] - acc[r]) : u_in[r];
+}
+
 // utils.py:308-330 command saturation (loop-invariant in open loop)
 F16_FD void clip_commands(const double (&u)[4], double (&uc)[4]) {
   uc[0] = clipd(u[0], 1000, 19000);
@@ -434,7 +486,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
 // K fused Euler steps of env.py::step from step k; stops (k < K on return) at the first state that fails step_ok or
 // leaves the tables.  The state is not advanced on the failing step.
 template <bool LQR, bool LIBM_TRIG>
-F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrLaw* lqr, double xcg, double dt,
+F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg, double dt,
                      int k, int K) {
   double uc[4];
   if (!LQR) clip_commands(u_in, uc);
@@ -446,7 +498,7 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
     double xd[18];
     if (LQR) {
       double u[4];
-      lqr_action(*lqr, x, u_in, u);
+      lqr_action_dense(*lqr, x, u_in, u);
       clip_commands(u, uc);
     }
     if (!calc_xdot_hifi<LIBM_TRIG>(img, x, uc, xcg, xd)) break;
@@ -466,7 +518,7 @@ F16_FD unsigned exact_status(const double (&x)[18], const double (&u_in)[4]) {
 
 // the whole step_batch semantics for one aircraft: returns the status word, k = steps taken
 template <bool LQR>
-F16_FD unsigned step_aircraft(const double* img, double (&x)[18], const double (&u_in)[4], const LqrLaw* lqr, double xcg,
+F16_FD unsigned step_aircraft(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg,
                               double dt, int K, int& k) {
   k = 0;
   if (either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3])) return K > 0 ? step_bounds(x, u_in) : 0u;

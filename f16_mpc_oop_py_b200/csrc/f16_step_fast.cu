@@ -8,7 +8,7 @@
 namespace f16 {
 namespace fast {
 
-__constant__ LqrLaw c_lqr_fast;
+__constant__ fastmath::LqrDense c_lqr_fast;
 
 // ------------------------------------------------------------------------------------------------------
 // step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
@@ -72,7 +72,11 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
                                   int* status, int* steps_done) {
   if (N <= 0) return cudaSuccess;
   if (lqr_host) {
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_lqr_fast, lqr_host, sizeof(LqrLaw), 0, cudaMemcpyHostToDevice, cfg.stream);
+    static fastmath::LqrDense dense;  // caller holds the library mutex; the copy is enqueued before the launch below
+    cudaError_t e = cudaStreamSynchronize(cfg.stream);  // a previous launch may still read the symbol's source
+    if (e != cudaSuccess) return e;
+    fastmath::make_dense_law(*lqr_host, dense);
+    e = cudaMemcpyToSymbolAsync(c_lqr_fast, &dense, sizeof(dense), 0, cudaMemcpyHostToDevice, cfg.stream);
     if (e != cudaSuccess) return e;
   }
   int threads = cfg.step_threads;

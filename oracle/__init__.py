@@ -152,6 +152,10 @@ class Oracle:
     def max_threads(self):
         return int(self.lib.orc_max_threads())
 
+    def set_threads(self, n):
+        """OpenMP team size of the batch loops (torchrun exports OMP_NUM_THREADS=1)."""
+        self.lib.orc_set_threads(int(n))
+
     # -- scalar pieces --------------------------------------------------------------------------
     def cell(self, axis, x):
         lo, hi = ctypes.c_int(), ctypes.c_int()

@@ -99,7 +99,9 @@ __attribute__((visibility("default"))) unsigned emu_step_fast(double* x_, const 
   for (int i = 0; i < 18; i++) x[i] = x_[i];
   for (int i = 0; i < 4; i++) u_in[i] = u_[i];
   int k = 0;
-  const unsigned st = lqr ? f16::fastmath::step_aircraft<true>(g_fast.data(), x, u_in, lqr, xcg, dt, K, k)
+  f16::fastmath::LqrDense dense;
+  if (lqr) f16::fastmath::make_dense_law(*lqr, dense);
+  const unsigned st = lqr ? f16::fastmath::step_aircraft<true>(g_fast.data(), x, u_in, &dense, xcg, dt, K, k)
                           : f16::fastmath::step_aircraft<false>(g_fast.data(), x, u_in, nullptr, xcg, dt, K, k);
   for (int i = 0; i < 18; i++) x_[i] = x[i];
   if (steps_done) *steps_done = k;

@@ -15,6 +15,10 @@ Fixtures
     xs, us, xdots     64 perturbed states/inputs and their _calc_xdot
     traj_x            state after 0,500,...,2000 F16.step calls from trim, open loop   env.py:105-130
     nl_xu, nl_xdot    parameters.py x0 (known-answer vector of SURVEY 8c) through Nlplant, hifi and lofi
+    Ad, Bd            cont2discrete(Ac, Bc, dt) (ZOH)                                   env.py:46
+    na_Ac, na_Bc, na_Ad, na_Bd   the reduced 9-state / 3-input model of env.py:49-60 (ssr)
+    na_x, na_u, na_xdots         16 reduced states/inputs and their F16._calc_xdot_na   env.py:152-193
+    K_lqr             F16._calc_LQR_gain(): -dlqr(Ad, Bd, C'C, I) on the reduced model  env.py:344-358, utils.py:219-245
 """
 import ctypes
 import os
@@ -60,6 +64,7 @@ def main():
 
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(0xF16)
+    rng_na = np.random.default_rng(0xF17)   # separate stream: the fixtures above keep their values
     for tag, so, fi in (("xcg25", "nlplant_xcg25.so", 1), ("xcg35", "nlplant_xcg35.so", 1),
                         ("lofi_xcg25", "nlplant_xcg25.so", 0)):
         lib = ctypes.CDLL(os.path.join(REF, "C", so))
@@ -95,7 +100,20 @@ def main():
             xd = np.zeros(18)
             lib.Nlplant(ctypes.c_void_p(nl_xu.ctypes.data), ctypes.c_void_p(xd.ctypes.data), ctypes.c_int(fid))
             nl.append(xd)
-        np.savez(os.path.join(OUT, f"env_{tag}.npz"), x_trim=x_trim, u_trim=u_trim, Ac=f16.ss.Ac, Bc=f16.ss.Bc,
+        # reduced (no-actuator) model: what feeds _calc_LQR_gain / _calc_MPC_action
+        f16.reset()
+        na_x, na_u, na_xdots = [], [], []
+        x_mpc0, u_mpc0 = f16.x._get_mpc_x(), f16.u._get_mpc_u()
+        for _ in range(16):
+            xm = x_mpc0 * (1 + 0.05 * rng_na.uniform(-1, 1, 9)) + np.where(x_mpc0 == 0, 0.05 * rng_na.uniform(-1, 1, 9), 0)
+            um = u_mpc0 * (1 + 0.2 * rng_na.uniform(-1, 1, 3))
+            na_x.append(xm)
+            na_u.append(um)
+            na_xdots.append(f16._calc_xdot_na(xm, um))
+        K_lqr = f16._calc_LQR_gain()
+        np.savez(os.path.join(OUT, f"env_{tag}.npz"), Ad=f16.ss.Ad, Bd=f16.ss.Bd, na_Ac=f16.ssr.Ac, na_Bc=f16.ssr.Bc,
+                 na_Ad=f16.ssr.Ad, na_Bd=f16.ssr.Bd, na_x=np.array(na_x), na_u=np.array(na_u), na_xdots=np.array(na_xdots),
+                 K_lqr=np.asarray(K_lqr), mpc_u_in_x_idx=np.array(f16.x._mpc_u_in_x_idx), x_trim=x_trim, u_trim=u_trim, Ac=f16.ss.Ac, Bc=f16.ss.Bc,
                  xdot_trim=xdot_trim, xs=np.array(xs), us=np.array(us), xdots=np.array(xdots), traj_x=np.array(traj),
                  nl_xu=nl_xu, nl_xdot=np.array(nl), fi=fi, xcg=0.35 if "35" in tag else 0.25,
                  mpc_x_idx=np.array(f16.x._mpc_x_idx), mpc_u_idx=np.array(f16.u._mpc_u_idx),
