@@ -305,6 +305,8 @@ def run_ours(args):
         L.f16_host_free_pinned(p)
 
     jac = None
+    if args.lin_variant is not None:
+        L.f16_set_linearise_variant(args.lin_variant)
     if not args.no_jacobians:
         jac = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 1)
         jac_fwd = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 0)
@@ -396,6 +398,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-jacobians", action="store_true", help="skip the linearise_batch (Jacobians/s) measurement")
     ap.add_argument("--jac-points", type=int, default=1 << 17, help="trim points per GPU in the Jacobian measurement")
+    ap.add_argument("--lin-variant", type=int, default=None, help="linearise kernel: 0 CTA per 32 aircraft, 1 warp per aircraft")
     ap.add_argument("--ref-aircraft", type=int, default=4096, help="aircraft in the CPU sample")
     ap.add_argument("--ref-euler-steps", type=int, default=200, help="Euler steps in the CPU sample")
     args = ap.parse_args()

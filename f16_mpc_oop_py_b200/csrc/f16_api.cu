@@ -53,6 +53,7 @@ struct State {
   int clr_mode = F16_CLR_AS_BUILT;
   bool smem_tables = true;
   int step_threads = 384;
+  int lin_variant = 0;
   double default_xcg = 0.25;
   int last_status = 0;
   unsigned long long launches = 0;
@@ -151,6 +152,7 @@ int init_locked(const char* table_path, int device) {
   if (const char* v = getenv("F16_CLR")) G.clr_mode = (!strcmp(v, "file") || !strcmp(v, "1")) ? F16_CLR_FROM_FILE : F16_CLR_AS_BUILT;
   if (const char* v = getenv("F16_STEP_THREADS")) G.step_threads = atoi(v);
   if (const char* v = getenv("F16_TABLE_STAGING")) G.smem_tables = atoi(v) != 0;
+  if (const char* v = getenv("F16_LIN_VARIANT")) G.lin_variant = atoi(v) == 1 ? 1 : 0;
 
   int rc = upload_tables();
   if (rc != F16_OK) return G.init_rc = rc;
@@ -169,6 +171,7 @@ f16::LaunchCfg cfg(bool smem_tables) {
   c.sm_count = G.sm_count;
   c.step_threads = G.step_threads;
   c.smem_tables = smem_tables;
+  c.lin_variant = G.lin_variant;
   c.launch_counter = &G.launches;
   return c;
 }
@@ -263,6 +266,13 @@ int f16_set_step_threads(int threads) {
   std::lock_guard<std::mutex> lk(G_mu);
   int prev = G.step_threads;
   G.step_threads = threads;
+  return prev;
+}
+
+int f16_set_linearise_variant(int variant) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.lin_variant;
+  G.lin_variant = variant == 1 ? 1 : 0;
   return prev;
 }
 

@@ -18,7 +18,7 @@
 #define F16_THREADS 384  // derivative-only kernels: one CTA per SM, 12 warps, <= 168 registers per thread
 // step_kernel is instantiated for 256 / 384 / 512 threads per CTA (254 / 168 / 128 registers per thread, one CTA
 // per SM because of the 105 KB table image); LaunchCfg::step_threads picks one at run time.
-#define F16_LIN_WARPS 12  // linearise: 12 warps x 32 aircraft per CTA, <= 170 registers per thread
+#define F16_LIN_WARPS 8    // linearise: 8 warps x 32 aircraft per CTA, <= 255 registers per thread (the staged evaluation holds 60 doubles of reusable stages)
 #define F16_LIN_TILE_LD 397  // doubles per aircraft in the output tile (396 + 1: conflict-free for both phases)
 
 namespace f16 {
@@ -145,9 +145,13 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
 
 // ------------------------------------------------------------------------------------------------------
 // linearise_batch: finite-difference A [18x18], B [18x4] of _calc_xdot (env.py:294-342).
-// CTA = 32 aircraft x F16_LIN_WARPS warps; warp w evaluates perturbation columns w, w+W, ... for the CTA's 32
-// aircraft (lane = aircraft, so every warp is column-uniform), results go to a padded shared tile and are
-// written out as contiguous [aircraft][18][18] / [aircraft][18][4] runs.
+// CTA = 32 aircraft x F16_LIN_WARPS warps, lane = aircraft, so every warp is column-uniform.
+//   phase A  four warps evaluate the stages of f at the unperturbed point (trig | atmos | alpha-beta tables | the other
+//            tables) into shared memory;
+//   phase B  warp w evaluates perturbation columns w, w+W, ...: calc_xdot_col recomputes only the stages the perturbed
+//            component feeds (f16_model.cuh) -- bit-identical to a full evaluation, a third of the work for most columns.
+//            npos / epos (columns 0, 1) feed nothing: those columns of A are exactly zero, as in the reference;
+//   phase C  the padded shared tile is written out as contiguous [aircraft][18][18] / [aircraft][18][4] runs.
 // ------------------------------------------------------------------------------------------------------
 template <int FI>
 struct LinSmem {
@@ -155,9 +159,23 @@ struct LinSmem {
   static constexpr int TILE_BYTES = 32 * F16_LIN_TILE_LD * 8;
   static constexpr int BASE_OFF = TILE_OFF + TILE_BYTES;  // f(x,u) per aircraft: [32][19]
   static constexpr int BASE_BYTES = 32 * 19 * 8;
-  static constexpr int STAT_OFF = BASE_OFF + BASE_BYTES;
-  static constexpr int TOTAL = STAT_OFF + 32 * 4;
+  static constexpr int STAGE_OFF = BASE_OFF + BASE_BYTES;  // XdotBase as [60][32]
+  static constexpr int STAGE_BYTES = XDOT_BASE_DOUBLES * 32 * 8;
+  static constexpr int STAT_OFF = STAGE_OFF + STAGE_BYTES;
+  static constexpr int TOTAL = STAT_OFF + 2 * 32 * 4;  // per-aircraft status, base-point envelope status
 };
+
+// XdotBase in shared memory as [field][lane]: fields 0..9 Trig, 10..15 the two Atmos, 16..59 Coef.  Explicit field lists
+// (no pointer casts) keep the struct in registers.  XB_COEF_AB = what hifi_coefs_ab writes, XB_COEF_REST = the others.
+#define XB_TRIG(X) X(0, tr.sa) X(1, tr.ca) X(2, tr.sb) X(3, tr.cb) X(4, tr.st) X(5, tr.ct) X(6, tr.sphi) X(7, tr.cphi) X(8, tr.spsi) X(9, tr.cpsi)
+#define XB_ATMOS(X) X(10, al.mach) X(11, al.qbar) X(12, al.ps) X(13, an.mach) X(14, an.qbar) X(15, an.ps)
+#define XB_COEF_AB(X) X(19, c.Cy) X(31, c.dCx_lef) X(32, c.dCz_lef) X(33, c.dCm_lef) X(34, c.dCy_lef) X(35, c.dCn_lef) X(36, c.dCl_lef) X(46, c.dCy_r30) X(47, c.dCn_r30) X(48, c.dCl_r30) X(49, c.dCy_a20) X(50, c.dCy_a20_lef) X(51, c.dCn_a20) X(52, c.dCn_a20_lef) X(53, c.dCl_a20) X(54, c.dCl_a20_lef)
+#define XB_COEF_REST(X) X(16, c.Cx) X(17, c.Cz) X(18, c.Cm) X(20, c.Cn) X(21, c.Cl) X(22, c.Cxq) X(23, c.Cyr) X(24, c.Cyp) X(25, c.Czq) X(26, c.Clr) X(27, c.Clp) X(28, c.Cmq) X(29, c.Cnr) X(30, c.Cnp) X(37, c.dCxq_lef) X(38, c.dCyr_lef) X(39, c.dCyp_lef) X(40, c.dCzq_lef) X(41, c.dClr_lef) X(42, c.dClp_lef) X(43, c.dCmq_lef) X(44, c.dCnr_lef) X(45, c.dCnp_lef) X(55, c.dCnbeta) X(56, c.dClbeta) X(57, c.dCm) X(58, c.eta_el) X(59, c.dCm_ds)
+#define XB_ST(k, f) stage[(k) * 32 + lane] = b.f;
+#define XB_LD(k, f) b.f = stage[(k) * 32 + lane];
+
+// evaluation order: the columns that recompute table look-ups or the atmosphere first (longest), the base point last
+__constant__ signed char c_lin_order[21] = {7, 8, 13, 2, 6, 14, 15, 3, 4, 5, 9, 10, 11, 12, 16, 17, 18, 19, 20, 21, 22};
 
 template <int FI>
 __global__ void __launch_bounds__(F16_LIN_WARPS * 32, 1)
@@ -167,78 +185,196 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
   const double* img = acquire_tables<FI, true>(tabs);
   double* tile = reinterpret_cast<double*>(f16_smem + LinSmem<FI>::TILE_OFF);
   double* base = reinterpret_cast<double*>(f16_smem + LinSmem<FI>::BASE_OFF);
+  double* stage = reinterpret_cast<double*>(f16_smem + LinSmem<FI>::STAGE_OFF);
   int* stat = reinterpret_cast<int*>(f16_smem + LinSmem<FI>::STAT_OFF);
+  int* stat0 = stat + 32;  // envelope status of the unperturbed point
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_groups = (N + 31) / 32;
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long n = grp * 32 + lane;
     const bool live = n < N;
     const int own = live ? owns<FI>(sel, n) : 0;
-    if (threadIdx.x < 32) stat[threadIdx.x] = (own < 0) ? (int)ST_FIDELITY : 0;
-    __syncthreads();
     double x0[18], u0[4];
 #pragma unroll
     for (int i = 0; i < 18; i++) x0[i] = live ? x_g[i * ld_x + n] : 0.0;
 #pragma unroll
     for (int i = 0; i < 4; i++) u0[i] = live ? u_g[i * ld_u + n] : 0.0;
     const double xcg = (live && sel.xcg) ? sel.xcg[n] : sel.xcg_default;
-    // columns 0..21 perturb x[0..17], u[0..3]; forward also needs column 22 = the unperturbed point
-    const int ncol = scheme == 0 ? 23 : 22;
-    for (int c = warp; c < ncol; c += F16_LIN_WARPS) {
-      if (own != 1) continue;
-      double x[18], u[4], fp[18], fm[18];
-      unsigned st = 0;
+    double xu0[17];
 #pragma unroll
-      for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? eps : 0.0);
-#pragma unroll
-      for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? eps : 0.0);
-      st |= calc_xdot<FI>(img, x, u, xcg, fp);
-      if (scheme != 0) {
-#pragma unroll
-        for (int i = 0; i < 18; i++) x[i] = x0[i] - (i == c ? eps : 0.0);
-#pragma unroll
-        for (int i = 0; i < 4; i++) u[i] = u0[i] - (i + 18 == c ? eps : 0.0);
-        st |= calc_xdot<FI>(img, x, u, xcg, fm);
-      }
-      if (st) {
-        atomicOr(&stat[lane], (int)st);
-#pragma unroll
-        for (int i = 0; i < 18; i++) fp[i] = qnan();
-      }
-      if (c == 22) {
-#pragma unroll
-        for (int r = 0; r < 18; r++) base[lane * 19 + r] = fp[r];
-      } else {
-#pragma unroll
-        for (int r = 0; r < 18; r++) {
-          const double v = scheme == 0 ? fp[r] : (fp[r] - fm[r]) / (2 * eps);
-          const int k = c < 18 ? r * 18 + c : 324 + r * 4 + (c - 18);
-          tile[lane * F16_LIN_TILE_LD + k] = v;
+    for (int i = 0; i < 17; i++) xu0[i] = x0[i];
+    const unsigned st_base = envelope_of<FI>(xu0);
+    if (threadIdx.x < 32) {
+      stat[lane] = (own < 0) ? (int)ST_FIDELITY : 0;
+      stat0[lane] = (int)st_base;
+    }
+    // ---- phase A: the stages of f at the unperturbed point ----
+    if (own == 1 && warp < 4) {
+      XdotBase b;
+      if (warp == 0) {
+        b.tr = trig_eval(xu0);
+        XB_TRIG(XB_ST)
+      } else if (warp == 1) {
+        atmos_pair(x0, b.al, b.an);
+        XB_ATMOS(XB_ST)
+      } else if (!st_base) {
+        const double r2d = 180.0 / 3.141592653589793;
+        const double alpha = xu0[7] * r2d, beta = xu0[8] * r2d;
+        if (FI == 1) {
+          const HifiLoc L = hifi_locate(img, alpha, beta, xu0[13]);
+          if (warp == 2) {
+            hifi_coefs_ab(img, L, b.c);
+            XB_COEF_AB(XB_ST)
+          } else {
+            hifi_coefs_rest(img, L, b.c);
+            XB_COEF_REST(XB_ST)
+          }
+        } else if (warp == 2) {
+          coef_eval<0>(img, alpha, beta, xu0[13], F16_DIVC(xu0[14], 21.5), F16_DIVC(xu0[15], 30.0), b.c);
+          XB_COEF_AB(XB_ST) XB_COEF_REST(XB_ST)
         }
       }
     }
     __syncthreads();
-    // write-out: 32 aircraft x 324 (A) and x 72 (B) contiguous doubles
+    // ---- phase B: perturbation columns ----
+    const int n_items = scheme == 0 ? 21 : 20;  // forward also needs the unperturbed point (last item)
+    for (int it = warp; it < n_items; it += F16_LIN_WARPS) {
+      if (own != 1) continue;
+      const int c = c_lin_order[it];
+      const int col = c == 22 ? -1 : c;
+      const bool reuse_coef = !col_feeds_coef<FI>(col);
+      double x[18], u[4], f[18];
+      XdotBase b;
+#pragma unroll
+      for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? eps : 0.0);
+#pragma unroll
+      for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? eps : 0.0);
+      XB_TRIG(XB_LD) XB_ATMOS(XB_LD)
+      if (reuse_coef) { XB_COEF_AB(XB_LD) XB_COEF_REST(XB_LD) }
+      unsigned st = calc_xdot_col<FI>(img, x, u, xcg, b, col, f);
+      double* out = c == 22 ? base + lane * 19 : tile + lane * F16_LIN_TILE_LD + (c < 18 ? c : 324 + (c - 18));
+      const int ld = c == 22 ? 1 : (c < 18 ? 18 : 4);
+      if (!st) {
+#pragma unroll
+        for (int r = 0; r < 18; r++) out[r * ld] = f[r];  // f(x + eps e_c); central: parked until f(x - eps e_c) is known
+      }
+      if (scheme != 0 && !st) {
+#pragma unroll
+        for (int i = 0; i < 18; i++) x[i] = x0[i] - (i == c ? eps : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = u0[i] - (i + 18 == c ? eps : 0.0);
+        XB_TRIG(XB_LD) XB_ATMOS(XB_LD)
+        if (reuse_coef) { XB_COEF_AB(XB_LD) XB_COEF_REST(XB_LD) }
+        st = calc_xdot_col<FI>(img, x, u, xcg, b, col, f);
+        if (!st) {
+#pragma unroll
+          for (int r = 0; r < 18; r++) out[r * ld] = (out[r * ld] - f[r]) / (2 * eps);
+        }
+      }
+      if (st) {
+        atomicOr(&stat[lane], (int)st);
+#pragma unroll
+        for (int r = 0; r < 18; r++) out[r * ld] = qnan();
+      }
+    }
+    __syncthreads();
+    // ---- phase C: write-out, 32 aircraft x 324 (A) and x 72 (B) contiguous doubles ----
     const long long n0 = grp * 32;
     const int n_here = (int)((N - n0) < 32 ? (N - n0) : 32);
-    for (int e = threadIdx.x; e < n_here * 324; e += blockDim.x) {
-      const int a = e / 324, k = e - a * 324;
+    // one warp per aircraft, lanes along the 396 contiguous output doubles (A then B): no per-element divisions
+    for (int a = warp; a < n_here; a += F16_LIN_WARPS) {
       if (owns<FI>(sel, n0 + a) == 0) continue;
-      double v = tile[a * F16_LIN_TILE_LD + k];
-      if (scheme == 0) v = (v - base[a * 19 + k / 18]) / eps;  // env.py:330
-      if (stat[a] & (int)ST_FIDELITY) v = qnan();
-      A_g[n0 * 324 + e] = v;
+      const bool void_all = (stat[a] & (int)ST_FIDELITY) != 0;
+      const double zero_col = stat0[a] ? qnan() : 0.0;  // d f / d npos, d f / d epos: f does not read them
+      const double* t = tile + a * F16_LIN_TILE_LD;
+      const double* f0 = base + a * 19;
+      double* Ao = A_g + (n0 + a) * 324;
+      double* Bo = B_g + (n0 + a) * 72;
+#pragma unroll
+      for (int j = 0; j < 11; j++) {  // 324 = 10 * 32 + 4
+        const int k = j * 32 + lane;
+        if (k < 324) {
+          const int r = k / 18, col = k - r * 18;
+          double v = t[k];
+          if (scheme == 0) v = (v - f0[r]) / eps;  // env.py:330
+          if (col < 2) v = zero_col;
+          if (void_all) v = qnan();
+          Ao[k] = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {  // 72 = 2 * 32 + 8
+        const int k = j * 32 + lane;
+        if (k < 72) {
+          double v = t[324 + k];
+          if (scheme == 0) v = (v - f0[k >> 2]) / eps;  // env.py:339
+          if (void_all) v = qnan();
+          Bo[k] = v;
+        }
+      }
     }
-    for (int e = threadIdx.x; e < n_here * 72; e += blockDim.x) {
-      const int a = e / 72, k = e - a * 72;
-      if (owns<FI>(sel, n0 + a) == 0) continue;
-      double v = tile[a * F16_LIN_TILE_LD + 324 + k];
-      if (scheme == 0) v = (v - base[a * 19 + k / 4]) / eps;  // env.py:339
-      if (stat[a] & (int)ST_FIDELITY) v = qnan();
-      B_g[n0 * 72 + e] = v;
-    }
-    if (status && threadIdx.x < n_here && owns<FI>(sel, n0 + threadIdx.x) != 0) status[n0 + threadIdx.x] = stat[threadIdx.x];
+    if (status && threadIdx.x < n_here && owns<FI>(sel, n0 + threadIdx.x) != 0)
+      status[n0 + threadIdx.x] = stat[threadIdx.x] | ((stat[threadIdx.x] & (int)ST_FIDELITY) ? 0 : stat0[threadIdx.x]);
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// linearise_batch, warp-per-aircraft variant: lane = perturbation column (0..17 states, 18..21 inputs, 22 = the
+// unperturbed point of the forward scheme), so one warp-wide evaluation of _calc_xdot yields every column of one
+// aircraft.  All lanes sit in the same table cell (shared-memory gathers broadcast), there is no shared output tile and
+// no CTA barrier; for a fixed row r the lanes write 18 (A) + 4 (B) consecutive doubles.  Forward differences take f(x)
+// from lane 22 by shuffle; central differences run the evaluation twice.
+// ------------------------------------------------------------------------------------------------------
+template <int FI>
+__global__ void __launch_bounds__(F16_THREADS, 1)
+linearise_warp_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x,
+                      const double* __restrict__ u_g, long long ld_u, long long N, double eps, int scheme,
+                      double* __restrict__ A_g, double* __restrict__ B_g, int* __restrict__ status) {
+  const double* img = acquire_tables<FI, true>(tabs);
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int ncol = scheme == 0 ? 23 : 22;
+  for (long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    double v[18];
+    unsigned st = own < 0 ? ST_FIDELITY : 0u;
+    if (own == 1 && lane < ncol) {
+      const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+      const int passes = scheme == 0 ? 1 : 2;
+#pragma unroll 1
+      for (int pass = 0; pass < passes; pass++) {
+        const double d = pass ? -eps : eps;
+        double x[18], u[4], f[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n] + (i == lane ? d : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = u_g[i * ld_u + n] + (i + 18 == lane ? d : 0.0);
+        st |= calc_xdot<FI>(img, x, u, xcg, f);
+#pragma unroll
+        for (int r = 0; r < 18; r++) v[r] = pass ? (v[r] - f[r]) / (2 * eps) : f[r];
+      }
+    }
+    if (scheme == 0) {  // env.py:330,339: (f(x + eps e_c) - f(x)) / eps; a failed f(x) voids every column
+      const unsigned st0 = __shfl_sync(0xffffffffu, st, 22);
+#pragma unroll
+      for (int r = 0; r < 18; r++) v[r] = (v[r] - __shfl_sync(0xffffffffu, v[r], 22)) / eps;
+      st |= st0;
+    }
+    if (st) {
+#pragma unroll
+      for (int r = 0; r < 18; r++) v[r] = qnan();
+    }
+    if (lane < 18) {
+#pragma unroll
+      for (int r = 0; r < 18; r++) A_g[n * 324 + r * 18 + lane] = v[r];
+    } else if (lane < 22) {
+#pragma unroll
+      for (int r = 0; r < 18; r++) B_g[n * 72 + r * 4 + (lane - 18)] = v[r];
+    }
+    const unsigned all = __reduce_or_sync(0xffffffffu, lane < ncol ? st : 0u);
+    if (status && lane == 0) status[n] = (int)all;
   }
 }
 
@@ -393,9 +529,18 @@ cudaError_t launch_linearise(const LaunchCfg& cfg, const DevTables& tabs, const 
                              long long ld_x, const double* u, long long ld_u, long long N, double eps, int scheme,
                              double* A, double* B, int* status) {
   if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (cfg.lin_variant == 1) {  // warp per aircraft
+    if (wants(sel, 1))
+      e = launch_persistent(cfg, linearise_warp_kernel<1>, F16_THREADS, table_smem<1>(true), N, F16_THREADS / 32, tabs, sel, x,
+                            ld_x, u, ld_u, N, eps, scheme, A, B, status);
+    if (e == cudaSuccess && wants(sel, 0))
+      e = launch_persistent(cfg, linearise_warp_kernel<0>, F16_THREADS, table_smem<0>(true), N, F16_THREADS / 32, tabs, sel, x,
+                            ld_x, u, ld_u, N, eps, scheme, A, B, status);
+    return e;
+  }
   const long long groups = (N + 31) / 32;
   const int threads = F16_LIN_WARPS * 32;
-  cudaError_t e = cudaSuccess;
   if (wants(sel, 1))
     e = launch_persistent(cfg, linearise_kernel<1>, threads, LinSmem<1>::TOTAL, groups, 1, tabs, sel, x, ld_x, u, ld_u,
                           N, eps, scheme, A, B, status);

@@ -26,6 +26,7 @@ struct LaunchCfg {
   int sm_count;
   int step_threads;  // CTA size of step_kernel: 256, 384 or 512
   bool smem_tables;  // stage tables in shared memory with TMA bulk copies (default) or read them through L1/L2
+  int lin_variant;   // linearise kernel: 0 = CTA per 32 aircraft with staged columns, 1 = warp per aircraft
   unsigned long long* launch_counter;
 };
 

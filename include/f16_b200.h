@@ -101,6 +101,8 @@ void f16_set_default_xcg(double xcg); /* for the legacy Nlplant symbol; default 
 int f16_set_table_staging(int mode);  /* 1 (default): tables staged in shared memory by TMA bulk copy;
                                          0: read through L1/L2 with ld.global.nc (for A/B measurements) */
 int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256, 384 (default), 512, 640, 768 or 1024 */
+int f16_set_linearise_variant(int variant); /* linearise_batch kernel: 0 = CTA per 32 aircraft, columns over warps, stages shared;
+                                               1 = warp per aircraft, column per lane.  Same bits either way. */
 /* sha256 (hex, 64 chars + NUL) of the canonical table payload in use */
 int f16_tables_sha256(char *out65);
 

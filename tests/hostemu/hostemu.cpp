@@ -114,4 +114,27 @@ __attribute__((visibility("default"))) void emu_fastmath_probe(double x, double 
   f16::fastmath::sincos_quarter(x, out[2], out[3]);
   out[4] = f16::fastmath::half_rho(g_fast.data(), tfac);
 }
+// linearise_kernel's staged evaluation: base stages at (x0,u0), then f at the point perturbed in component `col`
+__attribute__((visibility("default"))) unsigned emu_calc_xdot_col(const double* x0_, const double* u0_, int col, double delta,
+                                                                  double* xd_, int fi, double xcg) {
+  double x[18], u[4], xd[18], xu0[17];
+  for (int i = 0; i < 18; i++) x[i] = x0_[i];
+  for (int i = 0; i < 4; i++) u[i] = u0_[i];
+  for (int i = 0; i < 17; i++) xu0[i] = x[i];
+  const double* img = fi ? g_hifi.data() : g_lofi.data();
+  f16::XdotBase b;
+  b.tr = f16::trig_eval(xu0);
+  f16::atmos_pair(x, b.al, b.an);
+  const double r2d = 180.0 / 3.141592653589793;
+  const unsigned st0 = fi ? f16::envelope_of<1>(xu0) : f16::envelope_of<0>(xu0);
+  if (!st0) {
+    if (fi) f16::coef_eval<1>(img, xu0[7] * r2d, xu0[8] * r2d, xu0[13], xu0[14] / 21.5, xu0[15] / 30.0, b.c);
+    else f16::coef_eval<0>(img, xu0[7] * r2d, xu0[8] * r2d, xu0[13], xu0[14] / 21.5, xu0[15] / 30.0, b.c);
+  }
+  if (col >= 0 && col < 18) x[col] = x[col] + delta;
+  if (col >= 18) u[col - 18] = u[col - 18] + delta;
+  const unsigned st = fi ? f16::calc_xdot_col<1>(img, x, u, xcg, b, col, xd) : f16::calc_xdot_col<0>(img, x, u, xcg, b, col, xd);
+  for (int i = 0; i < 18; i++) xd_[i] = st ? __builtin_nan("") : xd[i];
+  return st;
+}
 }

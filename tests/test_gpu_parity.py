@@ -409,9 +409,38 @@ def test_linearise_matches_env_py_golden(f16, mode, golden):
     assert C.shape == (10, 18) and D.shape == (10, 4) and C.sum() == 10
 
 
+@pytest.fixture(params=[0, 1], ids=["cta32", "warp"])
+def lin_variant(request, f16):
+    """both linearise kernels: CTA per 32 aircraft with shared stages, and warp per aircraft"""
+    prev = f16.lib.f16_set_linearise_variant(request.param)
+    yield request.param
+    f16.lib.f16_set_linearise_variant(prev)
+
+
+def test_linearise_variants_bit_equal(f16):
+    """the staged evaluation (stages shared between columns) and the plain one give the same bits"""
+    g = load_golden("xcg25")
+    x, u = perturbed_trim(1000 + 7, g["x_trim"], seed=5, frac=0.04)
+    x[13, 5] = 25.0 - 1e-6
+    fi = np.ones(x.shape[1], dtype=np.uint8)
+    fi[::3] = 0
+    out = {}
+    for variant in (0, 1):
+        prev = f16.lib.f16_set_linearise_variant(variant)
+        for scheme in ("forward", "central"):
+            fb = f16.F16Batch(x, u, fi_flag=fi, xcg=0.25)
+            A, B, _, _ = fb.linearise(x, u, scheme=scheme)
+            out[variant, scheme] = (A, B, fb.last_status.copy())
+        f16.lib.f16_set_linearise_variant(prev)
+    for scheme in ("forward", "central"):
+        a, b = out[0, scheme], out[1, scheme]
+        assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+
+
 @pytest.mark.parametrize("scheme", ["forward", "central"])
 @pytest.mark.parametrize("fi", [1, 0])
-def test_linearise_batch_grid(f16, oracle, scheme, fi):
+def test_linearise_batch_grid(f16, oracle, scheme, fi, lin_variant):
     """a 16 x 16 altitude x velocity grid about perturbed trims (cfg 4 is 64 x 64; same code path)"""
     g = load_golden("xcg25")
     n = 256 + 13     # ragged last CTA
@@ -428,7 +457,7 @@ def test_linearise_batch_grid(f16, oracle, scheme, fi):
     assert np.abs(A[ok] - Ar[ok]).max() < TOL_JAC and np.abs(B[ok] - Br[ok]).max() < TOL_JAC
 
 
-def test_linearise_out_of_envelope_column_is_nan(f16):
+def test_linearise_out_of_envelope_column_is_nan(f16, lin_variant):
     g = load_golden("xcg25")
     x = np.repeat(g["x_trim"][:, None], 3, axis=1)
     u = np.repeat(g["u_trim"][:, None], 3, axis=1)

@@ -288,3 +288,28 @@ def test_fast_step_on_the_actuator_limits(emu_fast, oracle):
         assert scaled_err(x[:, None], ref) < 1e-7 if s else scaled_err(x[:, None], ref) < 1e-9
         assert np.all(x[12] >= 1000) and np.all(x[12] <= 19000) and abs(x[13]) <= 25 and abs(x[14]) <= 21.5 and abs(x[15]) <= 30
         assert 0 <= x[16] <= 25
+
+
+@pytest.mark.parametrize("fi", [1, 0])
+def test_staged_column_evaluation_bit_equal(emu, fi):
+    """linearise_batch reuses the stages a perturbation does not touch: f(x + delta e_col) through the staged path
+    must equal the plain _calc_xdot at the same point bit for bit, for every column, both signs, both fidelities."""
+    from _inputs import X_TRIM_XCG25, perturbed_trim
+    emu.emu_calc_xdot_col.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_double]
+    x0, u0 = perturbed_trim(24, X_TRIM_XCG25, seed=31, frac=0.04)
+    x0[13, 3] = 25.0 - 1e-6       # + eps leaves DH1
+    x0[8, 4] = np.deg2rad(30.0)   # + eps leaves BETA1, - eps is inside
+    for n in range(x0.shape[1]):
+        x, u = np.ascontiguousarray(x0[:, n]), np.ascontiguousarray(u0[:, n])
+        for col in range(-1, 22):
+            for delta in (1e-5, -1e-5):
+                xp, up = x.copy(), u.copy()
+                if 0 <= col < 18:
+                    xp[col] += delta
+                elif col >= 18:
+                    up[col - 18] += delta
+                ref, out = np.zeros(18), np.zeros(18)
+                s_ref = emu.emu_calc_xdot(_p(xp), _p(up), _p(ref), fi, 0.25)
+                s_out = emu.emu_calc_xdot_col(_p(x), _p(u), col, delta, _p(out), fi, 0.25)
+                assert s_ref == s_out, (n, col, delta)
+                assert np.array_equal(ref, out, equal_nan=True), (n, col, delta)
