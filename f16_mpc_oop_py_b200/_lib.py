@@ -67,6 +67,10 @@ def _load():
                                  c_vp, ctypes.c_int, c_vp, ctypes.c_double, c_vp, c_vp]
     L.linearise_batch_dev.argtypes = [c_vp, c_ll, c_vp, c_ll, c_ll, ctypes.c_double, ctypes.c_int, c_vp, c_vp, c_vp,
                                       ctypes.c_int, c_vp, ctypes.c_double, c_vp]
+    L.trim_batch.argtypes = [c_vp, c_vp, c_ll, ctypes.c_double, ctypes.c_int, c_vp, c_vp, c_vp] + sel + [c_vp]
+    L.trim_batch_dev.argtypes = [c_vp, c_vp, c_ll, ctypes.c_double, ctypes.c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, ctypes.c_int,
+                                 c_vp, ctypes.c_double, c_vp]
+    L.f16_set_linearise_variant.argtypes = [ctypes.c_int]
     L.f16_hifi_probe.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]
     L.f16_lofi_probe.argtypes = [c_vp] * 5 + [c_ll, c_vp]
     L.atmos_batch.argtypes = [c_vp, c_vp, c_ll, c_vp]

@@ -509,6 +509,51 @@ int linearise_batch(const double* x_soa, const double* u_soa, long long N, doubl
   return F16_OK;
 }
 
+// ---- trim_batch: env.py::trim for N flight conditions ------------------------------------------------------------
+static const double kTrimGuess[5] = {5000, -0.09, 8.49, -0.01, 0.01};  // env.py:264-271 (unpacked as P3, dh, da, dr, alpha)
+
+int trim_batch_dev(const double* h, const double* V, long long N, double tol, int maxiter, const double* ux0, double* x_trim_soa,
+                   long long ld_x, double* info_soa, long long ld_info, const unsigned char* fi, int fi_default, const double* xcg,
+                   double xcg_default, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!h || !V || !x_trim_soa)) || ld_x < N || (info_soa && ld_info < N) || !(tol >= 0) || maxiter < 1) {
+    set_err("trim_batch_dev: bad argument");
+    return F16_ERR_ARG;
+  }
+  CK(DISPATCH(launch_trim, cfg(G.smem_tables && N >= 1024), tabs(), sel_of(fi, fi_default, xcg, xcg_default), h, V, N, tol, maxiter,
+              ux0 ? ux0 : kTrimGuess, x_trim_soa, ld_x, info_soa, ld_info, status));
+  return F16_OK;
+}
+
+int trim_batch(const double* h, const double* V, long long N, double tol, int maxiter, const double* ux0, double* x_trim_soa,
+               double* info_soa, const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!h || !V || !x_trim_soa)) || !(tol >= 0) || maxiter < 1) { set_err("trim_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(2 * n * 8));
+  CK(G.b_out.reserve(18 * n * 8));
+  CK(G.b_a.reserve(4 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  double* d = (double*)G.b_in.p;
+  H2D(d, h, n * 8);
+  H2D(d + n, V, n * 8);
+  CK(DISPATCH(launch_trim, cfg(G.smem_tables && N >= 1024), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), d, d + n, N, tol,
+              maxiter, ux0 ? ux0 : kTrimGuess, (double*)G.b_out.p, N, (double*)G.b_a.p, N, (int*)G.b_st.p));
+  D2H(x_trim_soa, G.b_out.p, 18 * n * 8);
+  if (info_soa) D2H(info_soa, G.b_a.p, 4 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
 // ---- parity probes -----------------------------------------------------------------------------------------------
 int f16_hifi_probe(const double* alpha_deg, const double* beta_deg, const double* el, long long N, double* coef, int* cells,
                    int* status) {

@@ -379,6 +379,50 @@ linearise_warp_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------------
+// trim_batch: env.py::trim (Nelder-Mead, ~2000 objective evaluations) for N flight conditions, one thread each.
+// The simplex lives in registers (f16_model.cuh::nelder_mead_trim); lanes differ only in how many iterations they need.
+// ------------------------------------------------------------------------------------------------------
+#define F16_TRIM_THREADS 256
+struct TrimGuess {
+  double ux[5];
+};
+
+template <int FI, bool SMEM>
+__global__ void __launch_bounds__(F16_TRIM_THREADS, 1)
+trim_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ h_g, const double* __restrict__ v_g, long long N, double tol,
+            int maxiter, TrimGuess guess, double* __restrict__ x_g, long long ld_x, double* __restrict__ info_g, long long ld_info,
+            int* __restrict__ status) {
+  const double* img = acquire_tables<FI, SMEM>(tabs);
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    double x[18];
+    TrimResult r;
+    if (own == 1) {
+      double ux[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) ux[k] = guess.ux[k];
+      const TrimPoint t = trim_point(h_g[n], v_g[n]);
+      r = nelder_mead_trim<FI>(img, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux);
+      trim_state(t, ux, x);  // env.py:275-288: the optimiser's (unclipped) point
+    } else {
+      r.cost = qnan(); r.iterations = 0; r.fcalls = 0; r.converged = 0; r.status = ST_FIDELITY;
+#pragma unroll
+      for (int i = 0; i < 18; i++) x[i] = qnan();
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (info_g) {
+      info_g[n] = r.cost;
+      info_g[ld_info + n] = (double)r.iterations;
+      info_g[2 * ld_info + n] = (double)r.fcalls;
+      info_g[3 * ld_info + n] = (double)r.converged;
+    }
+    if (status) status[n] = (int)r.status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // parity probes
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -547,6 +591,23 @@ cudaError_t launch_linearise(const LaunchCfg& cfg, const DevTables& tabs, const 
   if (e == cudaSuccess && wants(sel, 0))
     e = launch_persistent(cfg, linearise_kernel<0>, threads, LinSmem<0>::TOTAL, groups, 1, tabs, sel, x, ld_x, u, ld_u,
                           N, eps, scheme, A, B, status);
+  return e;
+}
+
+cudaError_t launch_trim(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* h, const double* v,
+                        long long N, double tol, int maxiter, const double* ux0, double* x_trim, long long ld_x, double* info,
+                        long long ld_info, int* status) {
+  if (N <= 0) return cudaSuccess;
+  TrimGuess g;
+  for (int k = 0; k < 5; k++) g.ux[k] = ux0[k];
+  cudaError_t e = cudaSuccess;
+  const bool s = cfg.smem_tables;
+  if (wants(sel, 1))
+    e = launch_persistent(cfg, s ? trim_kernel<1, true> : trim_kernel<1, false>, F16_TRIM_THREADS, table_smem<1>(s), N,
+                          F16_TRIM_THREADS, tabs, sel, h, v, N, tol, maxiter, g, x_trim, ld_x, info, ld_info, status);
+  if (e == cudaSuccess && wants(sel, 0))
+    e = launch_persistent(cfg, s ? trim_kernel<0, true> : trim_kernel<0, false>, F16_TRIM_THREADS, table_smem<0>(s), N,
+                          F16_TRIM_THREADS, tabs, sel, h, v, N, tol, maxiter, g, x_trim, ld_x, info, ld_info, status);
   return e;
 }
 

@@ -85,6 +85,26 @@ def atmos(alt, vt):
     return out
 
 
+def trim(h_t, v_t, fi=1, xcg=0.25, tol=1e-10, maxiter=50000, ux0=None):
+    """trim_batch: env.py::trim(h_t, v_t) for arrays of altitudes [ft] and airspeeds [ft/s] (env.py:198-292).
+    -> (x_trim [18][N], opt) with opt = dict(fun, nit, nfev, success, status), the fields of scipy's OptimizeResult the
+    reference returns as `opt`."""
+    h, v = _c(np.atleast_1d(h_t)), _c(np.atleast_1d(v_t))
+    assert h.shape == v.shape and h.ndim == 1
+    n = h.size
+    fa, fd, xa, xd = _sel(fi, xcg, n)
+    x = np.empty((18, n))
+    info = np.empty((4, n))
+    st = np.zeros(n, dtype=np.int32)
+    g = None if ux0 is None else _c(ux0)
+    check(lib.trim_batch(_p(h), _p(v), n, float(tol), int(maxiter), _p(g), _p(x), _p(info),
+                         None if fa is None else fa.ctypes.data_as(_lib.c_ubp), fd,
+                         None if xa is None else xa.ctypes.data_as(_lib.c_dp), xd, _p(st)), "trim_batch")
+    opt = {"fun": info[0], "nit": info[1].astype(np.int64), "nfev": info[2].astype(np.int64),
+           "success": info[3] != 0, "status": st}
+    return x, opt
+
+
 class F16Batch:
     """N independent F-16s behind the reference's F16 interface (env.py:29-342)."""
 
@@ -135,6 +155,11 @@ class F16Batch:
         reward, isdone = 1, self.status != 0
         info = {'fidelity': 'high' if np.all(np.asarray(self.fi_flag) == 1) else 'mixed/low', 'status': self.status}
         return self.get_obs(self.x, self.u), reward, isdone, info
+
+    # env.py:198-292
+    def trim(self, h_t, v_t, **kw):
+        return trim(h_t, v_t, fi=self.fi_flag if np.ndim(self.fi_flag) == 0 else 1,
+                    xcg=self.xcg if np.ndim(self.xcg) == 0 else 0.25, **kw)
 
     # env.py:294-342
     def linearise(self, x, u, scheme='forward', eps=1e-5):

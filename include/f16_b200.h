@@ -123,6 +123,14 @@ int step_batch(double *x_soa, const double *u_soa, long long N, int K, double dt
 int linearise_batch(const double *x_soa, const double *u_soa, long long N, double eps, int scheme, double *A, double *B,
                     const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
 
+/* env.py::trim (env.py:198-292) for N flight conditions: h [N] ft, V [N] ft/s -> x_trim_soa [18][N], the state
+ * env.py:288 builds from the optimiser's output.  Nelder-Mead exactly as scipy runs it for the reference (env.py:273:
+ * tol -> xatol = fatol, maxiter, default coefficients, default initial simplex) from ux0 = {P3, dh, da, dr, alpha}
+ * (NULL = the reference's guess {5000, -0.09, 8.49, -0.01, 0.01}, env.py:264-271).  info_soa [4][N] (may be NULL) =
+ * cost, iterations, objective evaluations, converged.  status [N]: envelope status of the returned point. */
+int trim_batch(const double *h, const double *V, long long N, double tol, int maxiter, const double *ux0, double *x_trim_soa,
+               double *info_soa, const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
+
 /* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
 int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
                       int fi_default, const double *xcg, double xcg_default, long long N, int *status);
@@ -135,6 +143,10 @@ int step_batch_dev(double *x_soa, long long ld_x, const double *u_soa, long long
 int linearise_batch_dev(const double *x_soa, long long ld_x, const double *u_soa, long long ld_u, long long N, double eps,
                         int scheme, double *A, double *B, const unsigned char *fi, int fi_default, const double *xcg,
                         double xcg_default, int *status);
+
+int trim_batch_dev(const double *h, const double *V, long long N, double tol, int maxiter, const double *ux0 /* host */,
+                   double *x_trim_soa, long long ld_x, double *info_soa, long long ld_info, const unsigned char *fi,
+                   int fi_default, const double *xcg, double xcg_default, int *status);
 
 /* ---- parity probes (used by the tests; device work, host buffers) ------------------------------------ */
 /* For N query points (alpha_deg, beta_deg, el): coef [44][N] in the order of the reference aggregators

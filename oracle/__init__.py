@@ -118,6 +118,11 @@ class Oracle:
                                      ctypes.c_int, ctypes.c_double, ctypes.POINTER(LqrLaw), c_ip]
         L.orc_linearise_batch.argtypes = [ctypes.c_int, c_dp, c_dp, ctypes.c_longlong, ctypes.c_double, ctypes.c_int,
                                           c_dp, c_dp, ctypes.c_int, ctypes.c_double, c_ip]
+        L.orc_trim.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, c_dp, ctypes.c_double,
+                               ctypes.c_int, c_dp, c_dp]
+        L.orc_trim_cost.argtypes = [ctypes.c_int, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, c_dp]
+        L.orc_trim_batch.argtypes = [ctypes.c_int, c_dp, c_dp, ctypes.c_longlong, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int, c_dp, c_dp, c_ip]
         L.orc_max_threads.restype = ctypes.c_int
         rc = L.orc_init(blob.encode())
         if rc != 0:
@@ -148,6 +153,31 @@ class Oracle:
     def set_clr_mode(self, from_file):
         """0: CLr table = 0 as the reference binaries compute it; 1: CL1320 data as intended (see f16_oracle.c)."""
         self.lib.orc_set_clr_mode(int(bool(from_file)))
+
+    def trim(self, h, V, fi=1, xcg=0.25, tol=1e-10, maxiter=50000, backend=PORT, ux0=None):
+        """env.py::trim(h, V): -> (x_trim [18], {cost, iterations, fcalls, converged}, status)"""
+        x = np.zeros(18)
+        info = np.zeros(4)
+        u0 = None if ux0 is None else np.ascontiguousarray(ux0, dtype=np.float64).ctypes.data_as(c_dp)
+        st = self.lib.orc_trim(backend, float(h), float(V), int(fi), float(xcg), u0, float(tol), int(maxiter),
+                               x.ctypes.data_as(c_dp), info.ctypes.data_as(c_dp))
+        return x, dict(cost=info[0], iterations=int(info[1]), fcalls=int(info[2]), converged=bool(info[3])), int(st)
+
+    def trim_cost(self, ux, h, V, fi=1, xcg=0.25, backend=PORT):
+        ux = np.ascontiguousarray(ux, dtype=np.float64)
+        c = ctypes.c_double()
+        st = self.lib.orc_trim_cost(backend, ux.ctypes.data_as(c_dp), float(h), float(V), int(fi), float(xcg), ctypes.byref(c))
+        return c.value, int(st)
+
+    def trim_batch(self, h, V, fi=1, xcg=0.25, tol=1e-10, maxiter=50000, backend=PORT):
+        h, V = np.ascontiguousarray(h, dtype=np.float64), np.ascontiguousarray(V, dtype=np.float64)
+        n = h.size
+        x = np.empty((18, n))
+        info = np.empty((4, n))
+        st = np.zeros(n, dtype=np.int32)
+        self.lib.orc_trim_batch(backend, h.ctypes.data_as(c_dp), V.ctypes.data_as(c_dp), n, int(fi), float(xcg), float(tol),
+                                int(maxiter), x.ctypes.data_as(c_dp), info.ctypes.data_as(c_dp), st.ctypes.data_as(c_ip))
+        return x, info, st
 
     def max_threads(self):
         return int(self.lib.orc_max_threads())

@@ -137,4 +137,17 @@ __attribute__((visibility("default"))) unsigned emu_calc_xdot_col(const double* 
   for (int i = 0; i < 18; i++) xd_[i] = st ? __builtin_nan("") : xd[i];
   return st;
 }
+// trim (Nelder-Mead on the device arithmetic): x_trim[18], info = {cost, iterations, fcalls, converged}
+__attribute__((visibility("default"))) unsigned emu_trim(double h, double V, int fi, double xcg, double tol, int maxiter,
+                                                         double* x_trim, double* info) {
+  double ux[5] = {5000, -0.09, 8.49, -0.01, 0.01};
+  const f16::TrimPoint t = f16::trim_point(h, V);
+  const f16::TrimResult r = fi ? f16::nelder_mead_trim<1>(g_hifi.data(), t, xcg, tol, maxiter, ux)
+                               : f16::nelder_mead_trim<0>(g_lofi.data(), t, xcg, tol, maxiter, ux);
+  double x[18];
+  f16::trim_state(t, ux, x);
+  for (int i = 0; i < 18; i++) x_trim[i] = x[i];
+  info[0] = r.cost; info[1] = r.iterations; info[2] = r.fcalls; info[3] = r.converged;
+  return r.status;
+}
 }

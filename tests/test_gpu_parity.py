@@ -492,3 +492,75 @@ def test_full_size_batch_properties(f16, oracle, mode):
     fb.reset()
     fb.step(K=200)
     assert np.array_equal(fb.x, x1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# trim_batch (env.py:198-292): the step before linearise in BASELINE cfg 4
+# ---------------------------------------------------------------------------------------------------------
+TRIM_SCALE = np.array([1, 1, 1e4, 1, 1, 1, 1e2, 1, 1, 1, 1, 1, 1e3, 1, 1, 1, 1, 1.0])   # natural size of each trim-state entry
+
+
+def test_trim_matches_reference_golden(f16, mode, golden):
+    """F16.trim(10000, 700) of the unmodified reference.  Nelder-Mead amplifies last-bit differences of the objective
+    (CUDA's sin/cos/pow vs glibc's) into a different path to the same minimiser: agreement to 1e-6 of each entry's
+    natural size -- the reference itself moves by 3e-8 with the tie order of np.argsort (tests/test_oracle.py)."""
+    x, opt = f16.trim([10000.0], [700.0], fi=int(golden["fi"]), xcg=float(golden["xcg"]))
+    assert opt["success"][0] and opt["status"][0] == 0
+    assert np.max(np.abs(x[:, 0] - golden["x_trim"]) / TRIM_SCALE) < 1e-6
+    assert 500 < opt["nit"][0] < 5000
+
+
+@pytest.mark.parametrize("fi", [1, 0])
+def test_trim_batch_grid_vs_oracle(f16, oracle, fi):
+    """an 8 x 8 altitude x velocity grid (cfg 4 uses 64 x 64 over the same ranges, Nguyen_m/runF16Sim.m:33-39)"""
+    hh, vv = np.meshgrid(np.linspace(5000, 40000, 8), np.linspace(300, 900, 8), indexing="ij")
+    h, v = hh.ravel(), vv.ravel()
+    xr, info, rst = oracle.trim_batch(h, v, fi, 0.35, backend=checker(oracle))
+    x, opt = f16.trim(h, v, fi=fi, xcg=0.35)
+    assert np.array_equal(opt["status"], rst)
+    ok = (rst == 0) & (info[3] != 0)
+    assert ok.mean() > 0.9 and np.array_equal(opt["success"][ok], np.ones(ok.sum(), dtype=bool))
+    # same minimum: the cost agrees to the objective's own rounding everywhere ...
+    assert np.all(np.abs(opt["fun"][ok] - info[0][ok]) <= 1e-6 * info[0][ok] + 1e-12)
+    # ... and the same point, to 1e-5 of each entry's natural size where a trim exists (cost ~ 0).  A flight condition
+    # that cannot be trimmed (300 ft/s at 35000 ft: cost 0.045, thrust command below its 1000 lb clip, where the objective
+    # no longer depends on it) has a flat direction along which two Nelder-Mead runs stop 4e-5 apart.
+    err = np.max(np.abs(x - xr) / TRIM_SCALE[:, None], axis=0)
+    sharp = ok & (info[0] < 1e-5) & (xr[12] > 1000) & (xr[12] < 19000)
+    assert err[ok].max() < 1e-3
+    if fi == 1:
+        assert sharp.sum() >= 10
+    assert not sharp.any() or err[sharp].max() < 1e-5
+    # it IS a trim: the weighted derivatives of env.py:258-260, at the clipped point obj_func evaluates (env.py:240-250)
+    xc = x[:, ok].copy()
+    for i, (lo, hi) in zip((12, 13, 14, 15), ((1000, 19000), (-25, 25), (-21.5, 21.5), (-30, 30))):
+        xc[i] = np.clip(xc[i], lo, hi)
+    xc[7] = np.clip(xc[7], -20 * np.pi / 180, 90 * np.pi / 180)
+    fb = f16.F16Batch(xc, xc[12:16], fi_flag=fi, xcg=0.35)
+    xd = fb._calc_xdot(xc, xc[12:16])
+    w = np.array([0, 0, 5, 10, 10, 10, 2, 10, 10, 10, 10, 10.0])
+    assert np.allclose((w[:, None] * xd[:12] ** 2).sum(axis=0), opt["fun"][ok], rtol=1e-6, atol=1e-14)
+
+
+def test_trim_then_linearise_full_cfg4_grid(f16):
+    """BASELINE cfg 4 end to end on the device: 64 x 64 trims, then central A/B at every trim point"""
+    hh, vv = np.meshgrid(np.linspace(5000, 40000, 64), np.linspace(300, 900, 64), indexing="ij")
+    x, opt = f16.trim(hh.ravel(), vv.ravel(), fi=1, xcg=0.35)
+    ok = opt["success"] & (opt["status"] == 0)
+    assert ok.mean() > 0.95
+    assert np.all(x[2] == hh.ravel()) and np.all(x[6] == vv.ravel())
+    assert np.all(np.abs(x[7, ok]) < np.deg2rad(45)) and np.all((x[12, ok] >= 1000 - 1e-9) | (opt["fun"][ok] > 1e-3))
+    fb = f16.F16Batch(x[:, ok], x[12:16, ok], xcg=0.35)
+    A, B, _, _ = fb.linearise(x[:, ok], x[12:16, ok], scheme="central")
+    assert np.isfinite(A).all() and np.isfinite(B).all() and (fb.last_status == 0).all()
+    # actuator block of A is the first-order lags of utils.py:308-330 wherever no rate limit is active
+    assert np.allclose(A[:, 13, 13], -20.2) and np.allclose(A[:, 14, 14], -20.2) and np.allclose(A[:, 15, 15], -20.2)
+
+
+def test_trim_edges(f16):
+    x, opt = f16.trim(np.zeros(0), np.zeros(0))
+    assert x.shape == (18, 0)
+    x, opt = f16.trim([10000.0, 10000.0], [700.0, 700.0], fi=np.array([1, 7], dtype=np.uint8))
+    assert opt["status"][0] == 0 and opt["status"][1] == 1 << 22 and np.isnan(x[:, 1]).all()
+    x, opt = f16.trim([10000.0], [700.0], maxiter=25)
+    assert not opt["success"][0] and opt["nit"][0] == 25

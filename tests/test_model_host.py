@@ -313,3 +313,20 @@ def test_staged_column_evaluation_bit_equal(emu, fi):
                 s_out = emu.emu_calc_xdot_col(_p(x), _p(u), col, delta, _p(out), fi, 0.25)
                 assert s_ref == s_out, (n, col, delta)
                 assert np.array_equal(ref, out, equal_nan=True), (n, col, delta)
+
+
+def test_trim_nelder_mead_bit_equal(emu, oracle):
+    """the register-resident Nelder-Mead of the kernels (f16_model.cuh::nelder_mead_trim) is the oracle's, bit for bit"""
+    emu.emu_trim.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, dp, dp]
+    for h, V, fi, xcg in ((10000, 700, 1, 0.25), (10000, 700, 1, 0.35), (10000, 700, 0, 0.25), (5000, 300, 1, 0.35),
+                          (40000, 900, 1, 0.25), (20000, 500, 0, 0.35), (36000, 450, 1, 0.25)):
+        x, info = np.zeros(18), np.zeros(4)
+        st = emu.emu_trim(h, V, fi, xcg, 1e-10, 50000, _p(x), _p(info))
+        xr, ir, sr = oracle.trim(h, V, fi, xcg)
+        assert st == sr and np.array_equal(x, xr), (h, V, fi, xcg)
+        assert (info[0], int(info[1]), int(info[2]), bool(info[3])) == (ir["cost"], ir["iterations"], ir["fcalls"], ir["converged"])
+    # iteration cap: same partial answer
+    x, info = np.zeros(18), np.zeros(4)
+    emu.emu_trim(10000, 700, 1, 0.25, 1e-10, 40, _p(x), _p(info))
+    xr, ir, _ = oracle.trim(10000, 700, 1, 0.25, maxiter=40)
+    assert np.array_equal(x, xr) and int(info[1]) == 40 == ir["iterations"] and not ir["converged"]

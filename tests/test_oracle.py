@@ -196,3 +196,32 @@ def test_lqr_law_restates_env_py(oracle):
     xd_law, _ = oracle.calc_xdot_batch(x[:, None].copy(), np.concatenate(([g["u_trim"][0]], u_env))[:, None].copy(), 1, 0.25)
     xs, _ = oracle.step_batch(x[:, None].copy(), g["u_trim"][:, None].copy(), 1, 1.0, 1, 0.25, law)
     assert np.allclose((xs[:, 0] - x), xd_law[:, 0], rtol=1e-9, atol=1e-9)
+
+
+def test_trim_restates_env_py(oracle):
+    """orc_trim (obj_func + scipy's Nelder-Mead restated in C) against the trims of the unmodified reference
+    (tests/golden x_trim = F16.trim(10000, 700), env.py:198-292).  Bit-identical where the search never meets two
+    vertices of equal cost; where it does (hifi xcg 0.25, 1823rd evaluation, costs equal to the last bit) np.argsort's
+    SIMD network orders the tie differently from a stable sort and the two searches part by < 1e-7 -- the reference's
+    own answer depends on the sorting network numpy picks for the host CPU at that point."""
+    for tag, fi, xcg, exact in (("xcg25", 1, 0.25, False), ("xcg35", 1, 0.35, True), ("lofi_xcg25", 0, 0.25, True)):
+        g = load_golden(tag)
+        x, info, st = oracle.trim(10000, 700, fi, xcg)
+        assert st == 0 and info["converged"]
+        if exact:
+            assert np.array_equal(x, g["x_trim"]), tag
+        assert np.abs(x - g["x_trim"]).max() < 1e-7
+        c_ref, _ = oracle.trim_cost(g["x_trim"][[12, 13, 14, 15, 7]], 10000, 700, fi, xcg)
+        assert info["cost"] <= c_ref * (1 + 1e-9) + 1e-30
+    # SURVEY 8c known answer 2
+    x, _, _ = oracle.trim(10000, 700, 1, 0.25)
+    assert abs(x[7] - 0.02059010021) < 1e-10 and abs(x[12] - 2886.646841) < 1e-5 and abs(x[13] + 2.038517528) < 1e-8
+
+
+def test_trim_cost_is_obj_func_of_scipy_run(oracle):
+    """scipy's own Nelder-Mead on orc_trim_cost reproduces the reference trim bit for bit: the objective is faithful"""
+    from scipy.optimize import minimize
+    g = load_golden("xcg25")
+    opt = minimize(lambda ux: oracle.trim_cost(ux, 10000, 700, 1, 0.25)[0], [5000, -0.09, 8.49, -0.01, 0.01],
+                   method="Nelder-Mead", tol=1e-10, options={"maxiter": 5e4})
+    assert np.array_equal(opt.x, g["x_trim"][[12, 13, 14, 15, 7]])
