@@ -60,7 +60,7 @@ struct State {
   // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
-  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5;
 };
 
 State G;
@@ -214,7 +214,9 @@ void f16_shutdown(void) {
   if (!G.ready) return;
   cudaSetDevice(G.device);
   cudaStreamSynchronize(G.stream);
-  for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush}) b->release();
+  for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush, &G.b_l1, &G.b_l2,
+                    &G.b_l3, &G.b_l4, &G.b_l5})
+    b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
   if (G.d_hifi_fast) cudaFree(G.d_hifi_fast);
@@ -551,6 +553,161 @@ int trim_batch(const double* h, const double* V, long long N, double tol, int ma
   if (info_soa) D2H(info_soa, G.b_a.p, 4 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);
   CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+// ---- between linearise and the LQR law: reduced model, zero-order hold, discrete LQR gain --------------------------------
+static bool dims_ok(int n, int m) { return n >= 1 && m >= 1 && n <= 18 && n + m <= 22; }
+
+int reduce_jacobian_batch_dev(const double* A, long long N, double* A_na, double* B_na) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!A || !A_na || !B_na))) { set_err("reduce_jacobian_batch_dev: bad argument"); return F16_ERR_ARG; }
+  CK(f16::linalg::launch_reduce_jacobian(cfg(false), A, N, A_na, B_na));
+  return F16_OK;
+}
+
+int discretise_batch_dev(const double* A, const double* B, int n, int m, long long N, double dt, double* Ad, double* Bd) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !dims_ok(n, m) || (N > 0 && (!A || !B || !Ad || !Bd))) { set_err("discretise_batch_dev: bad argument"); return F16_ERR_ARG; }
+  CK(f16::linalg::launch_zoh(cfg(false), A, B, n, m, N, dt, Ad, Bd));
+  return F16_OK;
+}
+
+int dlqr_batch_dev(const double* Ad, const double* Bd, const double* Q /* device, n x n */, const double* R /* device, m x m */,
+                   int n, int m, long long N, double* K, double* P, int* info) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !dims_ok(n, m) || (N > 0 && (!Ad || !Bd || !Q || !R || !K))) { set_err("dlqr_batch_dev: bad argument"); return F16_ERR_ARG; }
+  CK(f16::linalg::launch_dlqr(cfg(false), Ad, Bd, Q, R, n, m, N, 64, 1e-15, K, P, info));
+  return F16_OK;
+}
+
+int reduce_jacobian_batch(const double* A, long long N, double* A_na, double* B_na) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!A || !A_na || !B_na))) { set_err("reduce_jacobian_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_l1.reserve(n * 324 * 8));
+  CK(G.b_l2.reserve(n * 81 * 8));
+  CK(G.b_l3.reserve(n * 27 * 8));
+  H2D(G.b_l1.p, A, n * 324 * 8);
+  CK(f16::linalg::launch_reduce_jacobian(cfg(false), (const double*)G.b_l1.p, N, (double*)G.b_l2.p, (double*)G.b_l3.p));
+  D2H(A_na, G.b_l2.p, n * 81 * 8);
+  D2H(B_na, G.b_l3.p, n * 27 * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int discretise_batch(const double* A, const double* B, int n, int m, long long N, double dt, double* Ad, double* Bd) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !dims_ok(n, m) || (N > 0 && (!A || !B || !Ad || !Bd))) { set_err("discretise_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t na = (size_t)N * n * n * 8, nb = (size_t)N * n * m * 8;
+  CK(G.b_l1.reserve(na));
+  CK(G.b_l2.reserve(nb));
+  CK(G.b_l3.reserve(na));
+  CK(G.b_l4.reserve(nb));
+  H2D(G.b_l1.p, A, na);
+  H2D(G.b_l2.p, B, nb);
+  CK(f16::linalg::launch_zoh(cfg(false), (const double*)G.b_l1.p, (const double*)G.b_l2.p, n, m, N, dt, (double*)G.b_l3.p,
+                             (double*)G.b_l4.p));
+  D2H(Ad, G.b_l3.p, na);
+  D2H(Bd, G.b_l4.p, nb);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int dlqr_batch(const double* Ad, const double* Bd, const double* Q, const double* R, int n, int m, long long N, double* K, double* P,
+               int* info) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !dims_ok(n, m) || (N > 0 && (!Ad || !Bd || !Q || !R || !K))) { set_err("dlqr_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t na = (size_t)N * n * n * 8, nb = (size_t)N * n * m * 8, nk = (size_t)N * m * n * 8;
+  CK(G.b_l1.reserve(na));
+  CK(G.b_l2.reserve(nb));
+  CK(G.b_l3.reserve(nk));
+  CK(G.b_l4.reserve(na));
+  CK(G.b_l5.reserve((size_t)(n * n + m * m) * 8));
+  CK(G.b_st.reserve((size_t)N * 8));
+  H2D(G.b_l1.p, Ad, na);
+  H2D(G.b_l2.p, Bd, nb);
+  double* dQ = (double*)G.b_l5.p;
+  H2D(dQ, Q, (size_t)n * n * 8);
+  H2D(dQ + n * n, R, (size_t)m * m * 8);
+  CK(f16::linalg::launch_dlqr(cfg(false), (const double*)G.b_l1.p, (const double*)G.b_l2.p, dQ, dQ + n * n, n, m, N, 64, 1e-15,
+                              (double*)G.b_l3.p, P ? (double*)G.b_l4.p : nullptr, info ? (int*)G.b_st.p : nullptr));
+  D2H(K, G.b_l3.p, nk);
+  if (P) D2H(P, G.b_l4.p, na);
+  if (info) D2H(info, G.b_st.p, (size_t)N * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+// F16._calc_LQR_gain (env.py:344-358) for N operating points, every stage on the device:
+// forward linearise -> reduced 9-state / 3-input model -> cont2discrete(dt) -> K = -dlqr(Ad, Bd, C'C = I, R = I)
+int lqr_gain_batch(const double* x_soa, const double* u_soa, long long N, double dt, double* K /* [N][3][9] */, const unsigned char* fi,
+                   int fi_default, const double* xcg, double xcg_default, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !K)) || !(dt > 0)) { set_err("lqr_gain_batch: bad argument"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(18 * n * 8));
+  CK(G.b_in2.reserve(4 * n * 8));
+  CK(G.b_a.reserve(324 * n * 8));
+  CK(G.b_b.reserve(72 * n * 8));
+  CK(G.b_st.reserve(n * 8));
+  CK(G.b_st2.reserve(n * 4));
+  CK(G.b_l1.reserve(n * 81 * 8));
+  CK(G.b_l2.reserve(n * 27 * 8));
+  CK(G.b_l3.reserve(n * 81 * 8));
+  CK(G.b_l4.reserve(n * 27 * 8));
+  CK(G.b_l5.reserve((81 + 9) * 8));
+  CK(G.b_out.reserve(n * 27 * 8));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  // the reduced model evaluates at X with the actuator states replaced by the inputs (env.py:175-177)
+  std::vector<double> xs(x_soa, x_soa + 18 * n);
+  for (int k = 0; k < 3; k++) memcpy(&xs[(13 + k) * n], &u_soa[(1 + k) * n], n * 8);
+  double QR[90];
+  for (int i = 0; i < 81; i++) QR[i] = (i % 10 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 9; i++) QR[81 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+  CK(cudaMemcpyAsync(G.b_in.p, xs.data(), 18 * n * 8, cudaMemcpyHostToDevice, G.stream));
+  CK(cudaStreamSynchronize(G.stream));  // xs is a temporary
+  H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  CK(cudaMemcpyAsync(G.b_l5.p, QR, sizeof QR, cudaMemcpyHostToDevice, G.stream));
+  CK(cudaStreamSynchronize(G.stream));  // QR is a temporary
+  CK(f16::strict::launch_linearise(cfg(true), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p, N,
+                                   (const double*)G.b_in2.p, N, N, 1e-5, F16_FD_FORWARD, (double*)G.b_a.p, (double*)G.b_b.p,
+                                   (int*)G.b_st2.p));
+  CK(f16::linalg::launch_reduce_jacobian(cfg(false), (const double*)G.b_a.p, N, (double*)G.b_l1.p, (double*)G.b_l2.p));
+  CK(f16::linalg::launch_zoh(cfg(false), (const double*)G.b_l1.p, (const double*)G.b_l2.p, 9, 3, N, dt, (double*)G.b_l3.p,
+                             (double*)G.b_l4.p));
+  double* dQ = (double*)G.b_l5.p;
+  CK(f16::linalg::launch_dlqr(cfg(false), (const double*)G.b_l3.p, (const double*)G.b_l4.p, dQ, dQ + 81, 9, 3, N, 64, 1e-15,
+                              (double*)G.b_out.p, nullptr, (int*)G.b_st.p));
+  std::vector<double> k(27 * n);
+  std::vector<int> info(2 * n), st(n);
+  CK(cudaMemcpyAsync(k.data(), G.b_out.p, 27 * n * 8, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(info.data(), G.b_st.p, n * 8, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(st.data(), G.b_st2.p, n * 4, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
+  for (size_t i = 0; i < 27 * n; i++) K[i] = -k[i];  // env.py:356: K = - dlqr(A, B, Q, R)
+  if (status)
+    for (size_t i = 0; i < n; i++) status[i] = st[i] ? st[i] : (info[2 * i] < 0 ? (int)F16_ST_NAN : 0);
   return F16_OK;
 }
 

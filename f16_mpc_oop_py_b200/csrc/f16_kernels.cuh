@@ -62,6 +62,15 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg&, const DevTables&, const Batc
                                   int* status, int* steps_done);
 }
 
+// f16_linalg.cu: reduced-model gather, zero-order-hold discretisation, discrete LQR gain (one thread per aircraft)
+namespace linalg {
+cudaError_t launch_reduce_jacobian(const LaunchCfg&, const double* A, long long N, double* A_na, double* B_na);
+cudaError_t launch_zoh(const LaunchCfg&, const double* A, const double* B, int n, int m, long long N, double dt, double* Ad,
+                       double* Bd);
+cudaError_t launch_dlqr(const LaunchCfg&, const double* Ad, const double* Bd, const double* Q, const double* R, int n, int m,
+                        long long N, int max_doublings, double tol, double* K, double* P, int* info);
+}  // namespace linalg
+
 // FP64 FMA micro-benchmark (f16_peak.cu): returns flops executed
 cudaError_t launch_dfma_peak(cudaStream_t stream, int sm_count, long long iters, double* sink, double* flops);
 

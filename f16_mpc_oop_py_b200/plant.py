@@ -105,6 +105,39 @@ def trim(h_t, v_t, fi=1, xcg=0.25, tol=1e-10, maxiter=50000, ux0=None):
     return x, opt
 
 
+def reduce_jacobian(A):
+    """A [N][18][18] -> (A_na [N][9][9], B_na [N][9][3]): the reduced model of env.py:49,152-193 (an exact gather)."""
+    A = _c(A).reshape(-1, 18, 18)
+    n = A.shape[0]
+    Ana, Bna = np.empty((n, 9, 9)), np.empty((n, 9, 3))
+    check(lib.reduce_jacobian_batch(_p(A), n, _p(Ana), _p(Bna)), "reduce_jacobian_batch")
+    return Ana, Bna
+
+
+def discretise(A, B, dt=P.dt):
+    """scipy.signal.cont2discrete((A, B, ., .), dt)[0:2] (zero-order hold, env.py:46,50) for stacks [N][n][n], [N][n][m]."""
+    A, B = _c(A), _c(B)
+    A = A.reshape((-1,) + A.shape[-2:])
+    B = B.reshape((-1,) + B.shape[-2:])
+    n, m = A.shape[1], B.shape[2]
+    Ad, Bd = np.empty_like(A), np.empty_like(B)
+    check(lib.discretise_batch(_p(A), _p(B), n, m, A.shape[0], float(dt), _p(Ad), _p(Bd)), "discretise_batch")
+    return Ad, Bd
+
+
+def dlqr(A, B, Q, R):
+    """utils.py:219-245 for stacks of discrete systems: K [N][m][n] (and P) with u = -K x; Q, R shared."""
+    A, B = _c(A), _c(B)
+    A = A.reshape((-1,) + A.shape[-2:])
+    B = B.reshape((-1,) + B.shape[-2:])
+    n, m = A.shape[1], B.shape[2]
+    Q, R = _c(Q).reshape(n, n), _c(R).reshape(m, m)
+    K, Pm = np.empty((A.shape[0], m, n)), np.empty_like(A)
+    info = np.zeros((A.shape[0], 2), dtype=np.int32)
+    check(lib.dlqr_batch(_p(A), _p(B), _p(Q), _p(R), n, m, A.shape[0], _p(K), _p(Pm), _p(info)), "dlqr_batch")
+    return K, Pm, info
+
+
 class F16Batch:
     """N independent F-16s behind the reference's F16 interface (env.py:29-342)."""
 
@@ -160,6 +193,18 @@ class F16Batch:
     def trim(self, h_t, v_t, **kw):
         return trim(h_t, v_t, fi=self.fi_flag if np.ndim(self.fi_flag) == 0 else 1,
                     xcg=self.xcg if np.ndim(self.xcg) == 0 else 0.25, **kw)
+
+    # env.py:344-358
+    def _calc_LQR_gain(self, x=None, u=None):
+        """K [N][3][9] = -dlqr(Ad, Bd, C'C, I) of the reduced model at (x, u) (default: the current state)."""
+        x = self.x if x is None else _c(x).reshape(18, -1)
+        u = self.u if u is None else _c(u).reshape(4, -1)
+        n = x.shape[1]
+        K = np.empty((n, 3, 9))
+        st = np.zeros(n, dtype=np.int32)
+        check(lib.lqr_gain_batch(_p(_c(x)), _p(_c(u)), n, float(self.dt), _p(K), *self._sel_c(), _p(st)), "lqr_gain_batch")
+        self.last_status = st
+        return K
 
     # env.py:294-342
     def linearise(self, x, u, scheme='forward', eps=1e-5):

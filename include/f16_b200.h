@@ -131,6 +131,22 @@ int linearise_batch(const double *x_soa, const double *u_soa, long long N, doubl
 int trim_batch(const double *h, const double *V, long long N, double tol, int maxiter, const double *ux0, double *x_trim_soa,
                double *info_soa, const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
 
+/* ---- between linearise and the control law (f16_linalg.cu) ---------------------------------------------------
+ * reduce_jacobian_batch: A [N][18][18] (forward linearise) -> the reference's 9-state / 3-input model (env.py:49,152-193):
+ *   A_na [N][9][9] over mpc_states {phi,theta,alpha,beta,p,q,r,lf1,lf2}, B_na [N][9][3] over {dh,da,dr}.  An exact gather:
+ *   _calc_xdot_na perturbs the same full-model evaluation (rows 3,4,7,8,9,10,11,16,17; the LEF derivatives swap, :184,189).
+ * discretise_batch: scipy.signal.cont2discrete(method='zoh') of env.py:46,50 for N systems, A [N][n][n], B [N][n][m].
+ * dlqr_batch: utils.py:219-245, K [N][m][n] = (B'PB + R)^-1 B'PA with P [N][n][n] (may be NULL) from the discrete Riccati
+ *   equation; Q [n][n], R [m][m] shared by all systems; info [N][2] = {0 ok / 1 not converged / <0 singular, doublings}.
+ * lqr_gain_batch: F16._calc_LQR_gain (env.py:344-358) for N operating points, device end to end: K [N][3][9] = -dlqr(...).
+ * n <= 18, n + m <= 22. */
+int reduce_jacobian_batch(const double *A, long long N, double *A_na, double *B_na);
+int discretise_batch(const double *A, const double *B, int n, int m, long long N, double dt, double *Ad, double *Bd);
+int dlqr_batch(const double *Ad, const double *Bd, const double *Q, const double *R, int n, int m, long long N, double *K,
+               double *P, int *info);
+int lqr_gain_batch(const double *x_soa, const double *u_soa, long long N, double dt, double *K, const unsigned char *fi,
+                   int fi_default, const double *xcg, double xcg_default, int *status);
+
 /* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
 int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
                       int fi_default, const double *xcg, double xcg_default, long long N, int *status);
@@ -147,6 +163,11 @@ int linearise_batch_dev(const double *x_soa, long long ld_x, const double *u_soa
 int trim_batch_dev(const double *h, const double *V, long long N, double tol, int maxiter, const double *ux0 /* host */,
                    double *x_trim_soa, long long ld_x, double *info_soa, long long ld_info, const unsigned char *fi,
                    int fi_default, const double *xcg, double xcg_default, int *status);
+
+int reduce_jacobian_batch_dev(const double *A, long long N, double *A_na, double *B_na);
+int discretise_batch_dev(const double *A, const double *B, int n, int m, long long N, double dt, double *Ad, double *Bd);
+int dlqr_batch_dev(const double *Ad, const double *Bd, const double *Q, const double *R, int n, int m, long long N, double *K,
+                   double *P, int *info);
 
 /* ---- parity probes (used by the tests; device work, host buffers) ------------------------------------ */
 /* For N query points (alpha_deg, beta_deg, el): coef [44][N] in the order of the reference aggregators

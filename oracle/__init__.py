@@ -250,3 +250,33 @@ def get_oracle():
     if _ORACLE is None:
         _ORACLE = Oracle()
     return _ORACLE
+
+
+# ---- between linearise and the control law: the reference does these with numpy / scipy (env.py:46-60,344-358, utils.py:219-245)
+NA_ROWS = [3, 4, 7, 8, 9, 10, 11, 16, 17]      # _calc_xdot_na output rows in full-state numbering (lf dots swapped, env.py:184,189)
+NA_COLS = [3, 4, 7, 8, 9, 10, 11, 17, 16]      # parameters.py:135 mpc_states
+NA_UCOLS = [13, 14, 15]                        # inputs written into the actuator states (env.py:175-177)
+
+
+def reduce_jacobian(A):
+    """A_na, B_na of F16.linearise(..., _calc_xdot_na) as a gather of the full forward-difference A (bit-identical: both
+    difference the same Nlplant evaluations; checked against the reference's own ssr in tests/test_oracle.py)."""
+    A = np.asarray(A)
+    return A[..., NA_ROWS, :][..., :, NA_COLS], A[..., NA_ROWS, :][..., :, NA_UCOLS]
+
+
+def discretise(A, B, dt):
+    """env.py:46,50: cont2discrete((A, B, C, D), dt)[0:2], scipy's own routine (zero-order hold via expm)"""
+    from scipy.signal import cont2discrete
+    n, m = A.shape[-1], B.shape[-1]
+    Ad, Bd = cont2discrete((A, B, np.eye(n), np.zeros((n, m))), dt)[0:2]
+    return Ad, Bd
+
+
+def dlqr(A, B, Q, R):
+    """utils.py:219-245 restated: P = solve_discrete_are(A, B, Q, R); K = inv(B'PB + R) (B'PA)"""
+    import scipy.linalg
+    P = np.array(scipy.linalg.solve_discrete_are(A, B, Q, R))
+    K = np.array(scipy.linalg.inv(B.T @ P @ B + R) @ (B.T @ P @ A))
+    return K, P
+

@@ -564,3 +564,73 @@ def test_trim_edges(f16):
     assert opt["status"][0] == 0 and opt["status"][1] == 1 << 22 and np.isnan(x[:, 1]).all()
     x, opt = f16.trim([10000.0], [700.0], maxiter=25)
     assert not opt["success"][0] and opt["nit"][0] == 25
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reduced model, zero-order hold, discrete LQR gain (env.py:46-60,344-358; utils.py:219-245)
+# ---------------------------------------------------------------------------------------------------------
+def test_reduced_jacobian_is_the_reference_ssr(f16, golden):
+    fb = f16.F16Batch(golden["x_trim"], golden["u_trim"], fi_flag=int(golden["fi"]), xcg=float(golden["xcg"]))
+    A, B, _, _ = fb.linearise(golden["x_trim"], golden["u_trim"], scheme="forward")
+    Ana, Bna = f16.reduce_jacobian(A)
+    from oracle import reduce_jacobian
+    ra, rb = reduce_jacobian(A)
+    assert np.array_equal(Ana, ra) and np.array_equal(Bna, rb)          # the gather itself is exact
+    assert np.abs(Ana[0] - golden["na_Ac"]).max() < TOL_JAC and np.abs(Bna[0] - golden["na_Bc"]).max() < TOL_JAC
+
+
+def test_discretise_matches_cont2discrete(f16, golden):
+    from oracle import discretise
+    for A, B, Ad_ref, Bd_ref in ((golden["Ac"], golden["Bc"], golden["Ad"], golden["Bd"]),
+                                 (golden["na_Ac"], golden["na_Bc"], golden["na_Ad"], golden["na_Bd"])):
+        Ad, Bd = f16.discretise(A, B, 0.001)
+        scale = max(np.abs(Ad_ref).max(), 1.0)
+        assert np.abs(Ad[0] - Ad_ref).max() < 1e-13 * scale and np.abs(Bd[0] - Bd_ref).max() < 1e-13 * scale
+    # a stack of random systems, small and large steps (scaling and squaring), against scipy
+    r = np.random.default_rng(3)
+    A = r.normal(size=(40, 18, 18)) * r.uniform(0.1, 30, size=(40, 1, 1))
+    B = r.normal(size=(40, 18, 4))
+    for dt in (0.001, 0.05, 0.5):
+        Ad, Bd = f16.discretise(A, B, dt)
+        for i in range(0, 40, 7):
+            ra, rb = discretise(A[i], B[i], dt)
+            s = max(np.abs(ra).max(), np.abs(rb).max(), 1.0)
+            assert np.abs(Ad[i] - ra).max() < 1e-11 * s and np.abs(Bd[i] - rb).max() < 1e-11 * s
+
+
+def test_dlqr_matches_reference_gain(f16, golden):
+    K, P, info = f16.dlqr(golden["na_Ad"], golden["na_Bd"], np.eye(9), np.eye(3))
+    assert info[0, 0] == 0 and 10 < info[0, 1] < 40
+    Kref = -golden["K_lqr"]
+    assert np.abs(K[0] - Kref).max() < 1e-9 * np.abs(Kref).max()
+    from oracle import dlqr
+    _, Pref = dlqr(golden["na_Ad"], golden["na_Bd"], np.eye(9), np.eye(3))
+    assert np.abs(P[0] - Pref).max() < 1e-9 * np.abs(Pref).max()
+
+
+def test_lqr_gain_batch_end_to_end(f16, golden):
+    """F16._calc_LQR_gain on the device: linearise -> reduce -> cont2discrete -> dlqr, against the reference's own K"""
+    fb = f16.F16Batch(golden["x_trim"], golden["u_trim"], fi_flag=int(golden["fi"]), xcg=float(golden["xcg"]))
+    K = fb._calc_LQR_gain()
+    assert K.shape == (1, 3, 9) and fb.last_status[0] == 0
+    # the gain inherits the 1e-10 finite-difference noise of A through a Riccati equation with cond(P) ~ 1e6
+    assert np.abs(K[0] - golden["K_lqr"]).max() < 1e-5 * np.abs(golden["K_lqr"]).max()
+
+
+def test_gain_scheduled_chain_over_a_trim_grid(f16):
+    """trim -> linearise -> reduce -> discretise -> dlqr over an 8 x 8 altitude x velocity grid; every closed loop is stable"""
+    hh, vv = np.meshgrid(np.linspace(5000, 30000, 8), np.linspace(400, 900, 8), indexing="ij")
+    x, opt = f16.trim(hh.ravel(), vv.ravel(), xcg=0.35)
+    ok = opt["success"] & (opt["status"] == 0) & (opt["fun"] < 1e-4)
+    assert ok.sum() > 40
+    fb = f16.F16Batch(x[:, ok], x[12:16, ok], xcg=0.35)
+    A, B, _, _ = fb.linearise(fb.x, fb.u, scheme="forward")
+    Ana, Bna = f16.reduce_jacobian(A)
+    Ad, Bd = f16.discretise(Ana, Bna, 0.001)
+    K, P, info = f16.dlqr(Ad, Bd, np.eye(9), np.eye(3))
+    assert (info[:, 0] == 0).all()
+    for i in range(K.shape[0]):
+        rho = np.abs(np.linalg.eigvals(Ad[i] - Bd[i] @ K[i])).max()
+        assert rho < 1.0
+    Kb = fb._calc_LQR_gain()
+    assert np.allclose(Kb, -K, rtol=1e-9, atol=1e-9)

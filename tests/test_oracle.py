@@ -225,3 +225,16 @@ def test_trim_cost_is_obj_func_of_scipy_run(oracle):
     opt = minimize(lambda ux: oracle.trim_cost(ux, 10000, 700, 1, 0.25)[0], [5000, -0.09, 8.49, -0.01, 0.01],
                    method="Nelder-Mead", tol=1e-10, options={"maxiter": 5e4})
     assert np.array_equal(opt.x, g["x_trim"][[12, 13, 14, 15, 7]])
+
+
+def test_reduced_model_and_control_chain_restated(golden):
+    """the numpy/scipy restatements of env.py:46-60,344-358 against what the reference itself produced (tests/golden)"""
+    from oracle import discretise, dlqr, reduce_jacobian
+    Ana, Bna = reduce_jacobian(golden["Ac"])
+    assert np.array_equal(Ana, golden["na_Ac"]) and np.array_equal(Bna, golden["na_Bc"])
+    Ad, Bd = discretise(golden["Ac"], golden["Bc"], 0.001)
+    assert np.array_equal(Ad, golden["Ad"]) and np.array_equal(Bd, golden["Bd"])
+    Ad, Bd = discretise(golden["na_Ac"], golden["na_Bc"], 0.001)
+    assert np.array_equal(Ad, golden["na_Ad"]) and np.array_equal(Bd, golden["na_Bd"])
+    K, _ = dlqr(golden["na_Ad"], golden["na_Bd"], np.eye(9), np.eye(3))
+    assert np.allclose(-K, golden["K_lqr"], rtol=1e-9, atol=1e-9)
