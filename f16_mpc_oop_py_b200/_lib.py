@@ -59,6 +59,7 @@ def _load():
     L.Nlplant_batch.argtypes = [c_vp, c_vp] + sel + [c_ll, c_vp]
     L.calc_xdot_batch.argtypes = [c_vp, c_vp, c_vp] + sel + [c_ll, c_vp]
     L.step_batch.argtypes = [c_vp, c_vp, c_ll, ctypes.c_int, ctypes.c_double, ctypes.POINTER(LqrLaw)] + sel + [c_vp, c_vp]
+    L.step_batch_traj.argtypes = [c_vp, c_vp, c_ll, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.POINTER(LqrLaw)] + sel + [c_vp, c_vp]
     L.linearise_batch.argtypes = [c_vp, c_vp, c_ll, ctypes.c_double, ctypes.c_int, c_vp, c_vp] + sel + [c_vp]
     L.Nlplant_batch_dev.argtypes = [c_vp, c_ll, c_vp, c_ll] + [c_vp, ctypes.c_int, c_vp, ctypes.c_double] + [c_ll, c_vp]
     L.calc_xdot_batch_dev.argtypes = [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, ctypes.c_int, c_vp, ctypes.c_double,

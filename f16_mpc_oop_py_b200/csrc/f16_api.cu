@@ -479,6 +479,53 @@ int step_batch(double* x_soa, const double* u_soa, long long N, int K, double dt
   return F16_OK;
 }
 
+// K Euler steps with a snapshot of the whole state every `snap_every` steps: traj [K / snap_every][18][N].
+// Launches of snap_every steps back to back on one stream (step_batch is restartable bit for bit at any K boundary),
+// each snapshot copied out while the next chunk runs.
+int step_batch_traj(double* x_soa, const double* u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t* lqr,
+                    const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, double* traj, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || K < 0 || snap_every < 1 || (N > 0 && (!x_soa || !u_soa || (!traj && K >= snap_every)))) {
+    set_err("step_batch_traj: bad argument");
+    return F16_ERR_ARG;
+  }
+  if (lqr && (lqr->n_sel < 0 || lqr->n_sel > 18)) { set_err("step_batch_traj: lqr.n_sel out of range"); return F16_ERR_ARG; }
+  if (lqr) for (int j = 0; j < lqr->n_sel; j++) if (lqr->sel[j] < 0 || lqr->sel[j] > 17) { set_err("step_batch_traj: lqr.sel out of range"); return F16_ERR_ARG; }
+  if (N == 0) return F16_OK;
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(18 * n * 8));
+  CK(G.b_in2.reserve(4 * n * 8));
+  CK(G.b_out.reserve(2 * 18 * n * 8));  // two snapshot slots: copy-out of one overlaps the next chunk
+  CK(G.b_st.reserve(n * 4));
+  const unsigned char* d_fi;
+  const double* d_xcg;
+  if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+  H2D(G.b_in.p, x_soa, 18 * n * 8);
+  H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  const bool smem = G.smem_tables && (N * (long long)snap_every >= 4096);
+  const f16::BatchSel sel = sel_of(d_fi, fi_default, d_xcg, xcg_default);
+  int done = 0, snap = 0;
+  while (done < K) {
+    const int k = (K - done) < snap_every ? (K - done) : snap_every;
+    CK(DISPATCH(launch_step, cfg(smem), tabs(), sel, (double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, k, dt,
+                reinterpret_cast<const f16::LqrLaw*>(lqr), (int*)G.b_st.p, nullptr));
+    done += k;
+    if (k == snap_every) {
+      double* slot = (double*)G.b_out.p + (size_t)(snap & 1) * 18 * n;
+      if (snap >= 2) CK(cudaStreamSynchronize(G.stream));  // the slot's previous copy-out has to be complete (same stream: it is)
+      CK(cudaMemcpyAsync(slot, G.b_in.p, 18 * n * 8, cudaMemcpyDeviceToDevice, G.stream));
+      CK(cudaMemcpyAsync(traj + (size_t)snap * 18 * n, slot, 18 * n * 8, cudaMemcpyDeviceToHost, G.stream));
+      snap++;
+    }
+  }
+  D2H(x_soa, G.b_in.p, 18 * n * 8);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
 int linearise_batch(const double* x_soa, const double* u_soa, long long N, double eps, int scheme, double* A, double* B,
                     const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, int* status) {
   std::lock_guard<std::mutex> lk(G_mu);

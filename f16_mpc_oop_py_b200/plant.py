@@ -194,6 +194,16 @@ class F16Batch:
         return trim(h_t, v_t, fi=self.fi_flag if np.ndim(self.fi_flag) == 0 else 1,
                     xcg=self.xcg if np.ndim(self.xcg) == 0 else 0.25, **kw)
 
+    # the driver loops of the reference (test_env.py:452-462, test_env_mk2.py:70-85): K steps, state stored every snap_every
+    def rollout(self, K, snap_every, lqr=None):
+        """-> traj [K // snap_every][18][N]; self.x, self.status end as after step(K=K)"""
+        ns = int(K) // int(snap_every)
+        traj = np.empty((ns, 18, self.n))
+        law = ctypes.byref(lqr) if lqr is not None else None
+        check(lib.step_batch_traj(_p(self.x), _p(self.u), self.n, int(K), int(snap_every), float(self.dt), law, *self._sel_c(),
+                                  _p(traj), _p(self.status)), "step_batch_traj")
+        return traj
+
     # env.py:344-358
     def _calc_LQR_gain(self, x=None, u=None):
         """K [N][3][9] = -dlqr(Ad, Bd, C'C, I) of the reduced model at (x, u) (default: the current state)."""

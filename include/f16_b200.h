@@ -118,6 +118,10 @@ int calc_xdot_batch(const double *x_soa, const double *u_soa, double *xdot_soa, 
 int step_batch(double *x_soa, const double *u_soa, long long N, int K, double dt, const f16_lqr_t *lqr,
                const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status,
                int *steps_done);
+/* step_batch with the whole state recorded every snap_every steps: traj [K / snap_every][18][N] (what the reference's
+ * drivers collect in x_storage, test_env.py:452-462).  Bit-identical to one step_batch call of K steps. */
+int step_batch_traj(double *x_soa, const double *u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t *lqr,
+                    const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, double *traj, int *status);
 /* Finite-difference Jacobians of _calc_xdot (env.py:294-342): A [N][18][18], B [N][18][4], row-major.
  * Always computed by the strict (no FMA contraction) build: the quotient amplifies rounding noise by 1/eps. */
 int linearise_batch(const double *x_soa, const double *u_soa, long long N, double eps, int scheme, double *A, double *B,

@@ -634,3 +634,30 @@ def test_gain_scheduled_chain_over_a_trim_grid(f16):
         assert rho < 1.0
     Kb = fb._calc_LQR_gain()
     assert np.allclose(Kb, -K, rtol=1e-9, atol=1e-9)
+
+
+def test_rollout_snapshots_equal_chunked_steps(f16, oracle, mode):
+    """step_batch_traj: snapshots every 250 steps of a 1000-step run = the states a user would get by calling step 4 times,
+    bit for bit, and the oracle's trajectory within tolerance; closed loop too"""
+    g = load_golden("xcg35")
+    x, u = perturbed_trim(300, g["x_trim"], seed=17)
+    sel = list(g["mpc_x_idx"])
+    law = f16.make_lqr(-g["K_lqr"], sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+    for lqr in (None, law):
+        fb = f16.F16Batch(x, u, xcg=0.35)
+        traj = fb.rollout(1000, 250, lqr=lqr)
+        fc = f16.F16Batch(x, u, xcg=0.35)
+        for s in range(4):
+            fc.step(K=250, lqr=lqr)
+            assert np.array_equal(traj[s], fc.x)
+        assert np.array_equal(fb.x, fc.x) and np.array_equal(fb.status, fc.status)
+        olaw = None if lqr is None else orc_make_lqr(-g["K_lqr"], sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+        ref, rst = oracle.step_batch(x, u, 500, 0.001, 1, 0.35, olaw, checker(oracle))
+        alive = (rst == 0) & (fb.status == 0)
+        assert alive.mean() > 0.5 and scaled_err(traj[1][:, alive], ref[:, alive]) < TOL_TRAJ
+    # K not a multiple of snap_every: the tail is still integrated
+    fb = f16.F16Batch(x, u, xcg=0.35)
+    traj = fb.rollout(130, 50)
+    fc = f16.F16Batch(x, u, xcg=0.35)
+    fc.step(K=130)
+    assert traj.shape[0] == 2 and np.array_equal(fb.x, fc.x)
