@@ -514,7 +514,7 @@ int step_batch_traj(double* x_soa, const double* u_soa, long long N, int K, int 
     done += k;
     if (k == snap_every) {
       double* slot = (double*)G.b_out.p + (size_t)(snap & 1) * 18 * n;
-      if (snap >= 2) CK(cudaStreamSynchronize(G.stream));  // the slot's previous copy-out has to be complete (same stream: it is)
+      // same stream: the slot's previous copy-out has completed before this copy starts
       CK(cudaMemcpyAsync(slot, G.b_in.p, 18 * n * 8, cudaMemcpyDeviceToDevice, G.stream));
       CK(cudaMemcpyAsync(traj + (size_t)snap * 18 * n, slot, 18 * n * 8, cudaMemcpyDeviceToHost, G.stream));
       snap++;

@@ -180,12 +180,14 @@ F16_FD double rcp_nr(double v) {
 }
 
 // cell and weight on a piecewise-uniform axis.  u = position in cell units (cell k spans [k, k+1], n cells).
-// floor(u) through the round-to-nearest of (u (1 - 2^-30) - 0.5) + 1.5*2^52: no conversion instruction, no
-// breakpoint load, and u == n lands in the last cell.  Within 2^-30 of a breakpoint the neighbouring cell may be
-// chosen with a weight just outside [0, 1]: the interpolant is continuous there, so the value moves by rounding only.
+// floor(u) through the round-to-nearest of (u (1 - 2^-30) - 0.5 + 2^-40) + 1.5*2^52: no conversion instruction, no
+// breakpoint load.  The 2^-30 shrink lands u == n in the last cell; the 2^-40 lift lands the bottom of the axis in
+// cell 0 even when the affine map to cell units rounds to -1e-16 there (fma(-20, 0.2, 4) = -2.2e-16).  Within those
+// margins of a breakpoint the neighbouring cell may be chosen with a weight just outside [0, 1]: the interpolant is
+// continuous there, so the value moves by rounding only.  The weight itself is exact: lam = u - k.
 F16_FD int cell_of(double u, int n_cells, double& lam) {
   const double magic = 6755399441055744.0;
-  const double tm = fma(u, K.shrink, -0.5) + magic;
+  const double tm = fma(u, K.shrink, -0.5 + 0x1p-40) + magic;
   lam = u - (tm - magic);
   int k = lo32(tm);
   k = k < 0 ? 0 : (k > n_cells - 1 ? n_cells - 1 : k);  // memory safety only; never active for in-envelope u

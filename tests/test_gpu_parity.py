@@ -661,3 +661,32 @@ def test_rollout_snapshots_equal_chunked_steps(f16, oracle, mode):
     fc = f16.F16Batch(x, u, xcg=0.35)
     fc.step(K=130)
     assert traj.shape[0] == 2 and np.array_equal(fb.x, fc.x)
+
+
+def test_step_on_the_envelope_corners(f16, oracle, mode):
+    """one Euler step from states exactly on the edges of every table axis (alpha -20 / 45 deg, beta +-30 deg, dele +-25 deg,
+    h 0 / 100000 ft) and within an ulp of interior breakpoints: the cell search of both builds must pick a valid cell"""
+    g = load_golden("xcg25")
+    d2r = np.pi / 180
+    alphas = [-20 * d2r, 45 * d2r, np.nextafter(45 * d2r, 0), 0.0, 5 * d2r, np.nextafter(5 * d2r, 1), np.nextafter(5 * d2r, -1)]
+    betas = [-30 * d2r, 30 * d2r, np.nextafter(30 * d2r, 0), -10 * d2r, 10 * d2r, 0.0, np.nextafter(10 * d2r, 1)]
+    els = [-25.0, 25.0, -10.0, 10.0, 0.0, np.nextafter(10.0, 0), np.nextafter(-10.0, 0)]
+    alts = [0.0, 100000.0, 35000.0, np.nextafter(35000.0, 0), 99999.0]
+    cases = []
+    for a in alphas:
+        for b in betas:
+            for e in els:
+                x = g["x_trim"].copy()
+                x[7], x[8], x[13] = a, b, e
+                x[2] = alts[len(cases) % len(alts)]
+                cases.append(x)
+    x = np.ascontiguousarray(np.array(cases).T)
+    u = np.ascontiguousarray(np.tile(g["u_trim"][:, None], (1, x.shape[1])))
+    ref, rst = oracle.step_batch(x, u, 1, 0.001, 1, 0.25, None, checker(oracle))
+    fb = f16.F16Batch(x, u, xcg=0.25)
+    fb.step(K=1)
+    assert np.array_equal(fb.status, rst)
+    ok = rst == 0
+    assert ok.sum() > 200
+    assert np.all(np.abs(fb.x[:, ok] - ref[:, ok]) <= 1e-13 * np.maximum(np.abs(ref[:, ok]), 1.0))
+    assert np.array_equal(fb.x[:, ~ok], x[:, ~ok])      # stopped aircraft keep their state

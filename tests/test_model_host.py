@@ -330,3 +330,38 @@ def test_trim_nelder_mead_bit_equal(emu, oracle):
     emu.emu_trim(10000, 700, 1, 0.25, 1e-10, 40, _p(x), _p(info))
     xr, ir, _ = oracle.trim(10000, 700, 1, 0.25, maxiter=40)
     assert np.array_equal(x, xr) and int(info[1]) == 40 == ir["iterations"] and not ir["converged"]
+
+
+def test_fast_calc_xdot_on_the_envelope_corners(emu_fast, oracle):
+    """the extreme cells of every table axis and of the tfac^4.14 table: exactly on alpha = -20 / 45 deg, beta = +-30 deg,
+    dele = +-25 deg, h = 0 / 100000 ft (cell search by rounding must land in the last cell, not beyond it), and within
+    an ulp of interior breakpoints"""
+    from _inputs import X_TRIM_XCG25
+    from conftest import scaled_err
+    d2r = np.pi / 180
+    alphas = [-20 * d2r, 45 * d2r, np.nextafter(45 * d2r, 0), 0.0, 5 * d2r, np.nextafter(5 * d2r, 1), np.nextafter(5 * d2r, -1)]
+    betas = [-30 * d2r, 30 * d2r, np.nextafter(30 * d2r, 0), -10 * d2r, 10 * d2r, 0.0, np.nextafter(10 * d2r, 1)]
+    els = [-25.0, 25.0, -10.0, 10.0, 0.0, np.nextafter(10.0, 0), np.nextafter(-10.0, 0)]
+    alts = [0.0, 100000.0, 35000.0, np.nextafter(35000.0, 0), 99999.0]
+    cases = []
+    for a in alphas:
+        for b in betas:
+            for e in els:
+                x = X_TRIM_XCG25.copy()
+                x[7], x[8], x[13] = a, b, e
+                x[2] = alts[len(cases) % len(alts)]
+                if x[7] * 180 / np.pi > 45 or abs(x[8] * 180 / np.pi) > 30:
+                    continue   # rounding of the degree conversion put it outside: covered by the status tests
+                cases.append(x)
+    X = np.ascontiguousarray(np.array(cases).T)
+    U = np.ascontiguousarray(np.tile(X_TRIM_XCG25[12:16][:, None], (1, X.shape[1])))
+    ref, st = oracle.calc_xdot_batch(X, U, 1, 0.25, PORT)
+    out = np.empty_like(ref)
+    for i in range(X.shape[1]):
+        xd = np.zeros(18)
+        s = emu_fast.emu_calc_xdot_fast(_p(np.ascontiguousarray(X[:, i])), _p(np.ascontiguousarray(U[:, i])), _p(xd), 0.25)
+        assert s == int(st[i]), i
+        out[:, i] = xd
+    ok = st == 0
+    assert ok.sum() > 200
+    assert scaled_err(out[:, ok], ref[:, ok]) < 1e-12
