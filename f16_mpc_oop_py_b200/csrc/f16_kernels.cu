@@ -159,23 +159,39 @@ struct LinSmem {
   static constexpr int TILE_BYTES = 32 * F16_LIN_TILE_LD * 8;
   static constexpr int BASE_OFF = TILE_OFF + TILE_BYTES;  // f(x,u) per aircraft: [32][19]
   static constexpr int BASE_BYTES = 32 * 19 * 8;
-  static constexpr int STAGE_OFF = BASE_OFF + BASE_BYTES;  // XdotBase as [60][32]
+  static constexpr int STAGE_OFF = BASE_OFF + BASE_BYTES;  // XdotBase as [61][32]
   static constexpr int STAGE_BYTES = XDOT_BASE_DOUBLES * 32 * 8;
   static constexpr int STAT_OFF = STAGE_OFF + STAGE_BYTES;
   static constexpr int TOTAL = STAT_OFF + 2 * 32 * 4;  // per-aircraft status, base-point envelope status
 };
 
-// XdotBase in shared memory as [field][lane]: fields 0..9 Trig, 10..15 the two Atmos, 16..59 Coef.  Explicit field lists
+// XdotBase in shared memory as [field][lane]: fields 0..9 and 60 Trig, 10..15 the two Atmos, 16..59 Coef.  Explicit field lists
 // (no pointer casts) keep the struct in registers.  XB_COEF_AB = what hifi_coefs_ab writes, XB_COEF_REST = the others.
-#define XB_TRIG(X) X(0, tr.sa) X(1, tr.ca) X(2, tr.sb) X(3, tr.cb) X(4, tr.st) X(5, tr.ct) X(6, tr.sphi) X(7, tr.cphi) X(8, tr.spsi) X(9, tr.cpsi)
+#define XB_TRIG(X) X(0, tr.sa) X(1, tr.ca) X(2, tr.sb) X(3, tr.cb) X(4, tr.st) X(5, tr.ct) X(6, tr.sphi) X(7, tr.cphi) X(8, tr.spsi) X(9, tr.cpsi) X(60, tr.tt)
 #define XB_ATMOS(X) X(10, al.mach) X(11, al.qbar) X(12, al.ps) X(13, an.mach) X(14, an.qbar) X(15, an.ps)
 #define XB_COEF_AB(X) X(19, c.Cy) X(31, c.dCx_lef) X(32, c.dCz_lef) X(33, c.dCm_lef) X(34, c.dCy_lef) X(35, c.dCn_lef) X(36, c.dCl_lef) X(46, c.dCy_r30) X(47, c.dCn_r30) X(48, c.dCl_r30) X(49, c.dCy_a20) X(50, c.dCy_a20_lef) X(51, c.dCn_a20) X(52, c.dCn_a20_lef) X(53, c.dCl_a20) X(54, c.dCl_a20_lef)
 #define XB_COEF_REST(X) X(16, c.Cx) X(17, c.Cz) X(18, c.Cm) X(20, c.Cn) X(21, c.Cl) X(22, c.Cxq) X(23, c.Cyr) X(24, c.Cyp) X(25, c.Czq) X(26, c.Clr) X(27, c.Clp) X(28, c.Cmq) X(29, c.Cnr) X(30, c.Cnp) X(37, c.dCxq_lef) X(38, c.dCyr_lef) X(39, c.dCyp_lef) X(40, c.dCzq_lef) X(41, c.dClr_lef) X(42, c.dClp_lef) X(43, c.dCmq_lef) X(44, c.dCnr_lef) X(45, c.dCnp_lef) X(55, c.dCnbeta) X(56, c.dClbeta) X(57, c.dCm) X(58, c.eta_el) X(59, c.dCm_ds)
 #define XB_ST(k, f) stage[(k) * 32 + lane] = b.f;
 #define XB_LD(k, f) b.f = stage[(k) * 32 + lane];
 
-// evaluation order: the columns that recompute table look-ups or the atmosphere first (longest), the base point last
-__constant__ signed char c_lin_order[21] = {7, 8, 13, 2, 6, 14, 15, 3, 4, 5, 9, 10, 11, 12, 16, 17, 18, 19, 20, 21, 22};
+// The quotient of the finite difference, (f(x + eps e_c) - f(x)) / eps (env.py:330,339) or (f+ - f-) / (2 eps): the IEEE
+// quotient through div_by (f16_model.cuh) -- most entries of a Jacobian are exactly 0, which the compiler's division
+// sequence sends down its slow path.  Steps outside [1e-15, 1e15] use the plain division.
+struct FdQuot {
+  double den, rden;
+  bool inv_ok;
+  __device__ __forceinline__ FdQuot(double eps, int scheme) {
+    den = scheme == 0 ? eps : 2 * eps;
+    rden = 1.0 / den;
+    inv_ok = den >= 1e-15 && den <= 1e15;
+  }
+  __device__ __forceinline__ double operator()(double num) const { return inv_ok ? div_by(num, den, rden) : num / den; }
+};
+
+// evaluation order, dealt round-robin to the warps (a pass costs about the same whatever it recomputes: measured, a deal
+// balanced by estimated cost was slower); the base point last
+
+__constant__ signed char c_lin_order[16] = {7, 8, 13, 2, 6, 14, 15, 3, 4, 5, 9, 10, 11, 12, 16, 22};
 
 template <int FI>
 __global__ void __launch_bounds__(F16_LIN_WARPS * 32, 1)
@@ -189,6 +205,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
   int* stat = reinterpret_cast<int*>(f16_smem + LinSmem<FI>::STAT_OFF);
   int* stat0 = stat + 32;  // envelope status of the unperturbed point
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const FdQuot fd(eps, scheme);
   const long long n_groups = (N + 31) / 32;
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long n = grp * 32 + lane;
@@ -237,7 +254,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
     }
     __syncthreads();
     // ---- phase B: perturbation columns ----
-    const int n_items = scheme == 0 ? 21 : 20;  // forward also needs the unperturbed point (last item)
+    const int n_items = scheme == 0 ? 16 : 15;  // columns 2..16; forward also needs the unperturbed point (last item)
     for (int it = warp; it < n_items; it += F16_LIN_WARPS) {
       if (own != 1) continue;
       const int c = c_lin_order[it];
@@ -268,13 +285,50 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         st = calc_xdot_col<FI>(img, x, u, xcg, b, col, f);
         if (!st) {
 #pragma unroll
-          for (int r = 0; r < 18; r++) out[r * ld] = (out[r * ld] - f[r]) / (2 * eps);
+          for (int r = 0; r < 18; r++) out[r * ld] = fd(out[r * ld] - f[r]);
         }
       }
       if (st) {
         atomicOr(&stat[lane], (int)st);
 #pragma unroll
         for (int r = 0; r < 18; r++) out[r * ld] = qnan();
+      }
+    }
+    // columns 17 (lf1) and 18..21 (the inputs) reach f through actuator_xdot only: rows 0..11 are exact zeros (identical
+    // bits on both sides of the difference) and rows 12..17 need no Nlplant evaluation -- a quarter of the passes saved
+    if (own == 1 && warp >= 3) {
+      const int c = 17 + (warp - 3);
+      double* out = tile + lane * F16_LIN_TILE_LD + (c < 18 ? c : 324 + (c - 18));
+      const int ld = c < 18 ? 18 : 4;
+      if (st_base) {
+        atomicOr(&stat[lane], (int)st_base);
+#pragma unroll
+        for (int r = 0; r < 18; r++) out[r * ld] = qnan();
+      } else {
+        Atmos al;
+        al.mach = stage[10 * 32 + lane];
+        al.qbar = stage[11 * 32 + lane];
+        al.ps = stage[12 * 32 + lane];
+        double x[18], u[4], f[18], g[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? eps : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? eps : 0.0);
+        actuator_xdot(x, u, al, f);
+        if (scheme == 0) {
+#pragma unroll
+          for (int r = 12; r < 18; r++) out[r * ld] = f[r];  // rows 0..11: the write-out knows they are zero
+        } else {
+#pragma unroll
+          for (int i = 0; i < 18; i++) x[i] = x0[i] - (i == c ? eps : 0.0);
+#pragma unroll
+          for (int i = 0; i < 4; i++) u[i] = u0[i] - (i + 18 == c ? eps : 0.0);
+          actuator_xdot(x, u, al, g);
+#pragma unroll
+          for (int r = 0; r < 12; r++) out[r * ld] = 0.0;
+#pragma unroll
+          for (int r = 12; r < 18; r++) out[r * ld] = fd(f[r] - g[r]);
+        }
       }
     }
     __syncthreads();
@@ -296,7 +350,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         if (k < 324) {
           const int r = k / 18, col = k - r * 18;
           double v = t[k];
-          if (scheme == 0) v = (v - f0[r]) / eps;  // env.py:330
+          if (scheme == 0) v = (col == 17 && r < 12) ? zero_col : fd(v - f0[r]);  // env.py:330
           if (col < 2) v = zero_col;
           if (void_all) v = qnan();
           Ao[k] = v;
@@ -307,7 +361,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         const int k = j * 32 + lane;
         if (k < 72) {
           double v = t[324 + k];
-          if (scheme == 0) v = (v - f0[k >> 2]) / eps;  // env.py:339
+          if (scheme == 0) v = k < 48 ? zero_col : fd(v - f0[k >> 2]);  // env.py:339; rows 0..11 of B are zero
           if (void_all) v = qnan();
           Bo[k] = v;
         }
@@ -335,6 +389,7 @@ linearise_warp_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int ncol = scheme == 0 ? 23 : 22;
+  const FdQuot fd(eps, scheme);
   for (long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
     const int own = owns<FI>(sel, n);
     if (own == 0) continue;
@@ -353,13 +408,13 @@ linearise_warp_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
         for (int i = 0; i < 4; i++) u[i] = u_g[i * ld_u + n] + (i + 18 == lane ? d : 0.0);
         st |= calc_xdot<FI>(img, x, u, xcg, f);
 #pragma unroll
-        for (int r = 0; r < 18; r++) v[r] = pass ? (v[r] - f[r]) / (2 * eps) : f[r];
+        for (int r = 0; r < 18; r++) v[r] = pass ? fd(v[r] - f[r]) : f[r];
       }
     }
     if (scheme == 0) {  // env.py:330,339: (f(x + eps e_c) - f(x)) / eps; a failed f(x) voids every column
       const unsigned st0 = __shfl_sync(0xffffffffu, st, 22);
 #pragma unroll
-      for (int r = 0; r < 18; r++) v[r] = (v[r] - __shfl_sync(0xffffffffu, v[r], 22)) / eps;
+      for (int r = 0; r < 18; r++) v[r] = fd(v[r] - __shfl_sync(0xffffffffu, v[r], 22));
       st |= st0;
     }
     if (st) {

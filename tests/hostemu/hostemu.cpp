@@ -150,4 +150,9 @@ __attribute__((visibility("default"))) unsigned emu_trim(double h, double V, int
   info[0] = r.cost; info[1] = r.iterations; info[2] = r.fcalls; info[3] = r.converged;
   return r.status;
 }
+// div_by (exact division through a rounded reciprocal) on n numerators: out[i] = the device arithmetic's a[i] / y
+__attribute__((visibility("default"))) void emu_div_by(const double* a, long long n, double y, double* out) {
+  const double r = 1.0 / y;
+  for (long long i = 0; i < n; i++) out[i] = f16::div_by(a[i], y, r);
+}
 }

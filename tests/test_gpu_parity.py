@@ -433,9 +433,10 @@ def test_linearise_variants_bit_equal(f16):
             out[variant, scheme] = (A, B, fb.last_status.copy())
         f16.lib.f16_set_linearise_variant(prev)
     for scheme in ("forward", "central"):
-        a, b = out[0, scheme], out[1, scheme]
-        assert np.array_equal(a[2], b[2])
-        assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+        for other in (1,):
+            a, b = out[0, scheme], out[other, scheme]
+            assert np.array_equal(a[2], b[2])
+            assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
 
 
 @pytest.mark.parametrize("scheme", ["forward", "central"])
