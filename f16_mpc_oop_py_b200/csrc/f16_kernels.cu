@@ -40,6 +40,45 @@ __device__ __forceinline__ const double* acquire_tables(const DevTables& t) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Input pipeline of the one-shot kernels (Nlplant_batch, calc_xdot_batch).  One evaluation per aircraft makes them
+// HBM-bound (280-324 B per aircraft); with plain loads a warp's memory phase and its ~1500-instruction compute phase
+// alternate and the bytes in flight per SM cover only half of the bandwidth-latency product.  Here every warp owns
+// NP x 32 doubles of shared memory and copies the input planes of the aircraft it takes NEXT with cp.async (8 bytes per
+// lane and plane: one 256-byte transaction per warp and plane) before it starts computing the current one, so the loads
+// of iteration i + 1 are in flight during the arithmetic of iteration i.  A lane reads back only what it copied itself:
+// no barrier, the warps stay independent.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+template <int NA, int NB>
+__device__ __forceinline__ void pipe_issue(double* buf, int lane, const double* __restrict__ a, long long lda,
+                                           const double* __restrict__ b, long long ldb, long long n, bool valid) {
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < NA; i++) cp_async8(buf + i * 32 + lane, a + i * lda + n);
+#pragma unroll
+    for (int i = 0; i < NB; i++) cp_async8(buf + (NA + i) * 32 + lane, b + i * ldb + n);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NP>
+__device__ __forceinline__ void pipe_take(const double* buf, int lane, double (&v)[NP]) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < NP; i++) v[i] = buf[i * 32 + lane];
+  asm volatile("" ::: "memory");  // the reads stay above the next cp.async into the same slots
+}
+
+template <int FI, bool SMEM, int NP>
+struct PipeSmem {
+  static constexpr int OFF = SMEM ? (Img<FI>::SMEM_BYTES + 127) / 128 * 128 : 0;
+  static constexpr int TOTAL = OFF + (F16_THREADS / 32) * NP * 32 * 8;
+};
+
+// ------------------------------------------------------------------------------------------------------
 // Nlplant_batch: xu [17][N] -> xdot [18][N]
 // ------------------------------------------------------------------------------------------------------
 template <int FI, bool SMEM>
@@ -47,12 +86,17 @@ __global__ void __launch_bounds__(F16_THREADS, 1)
 nlplant_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ xu_g, long long ld_in, double* __restrict__ xd_g,
                long long ld_out, long long N, int* __restrict__ status) {
   const double* img = acquire_tables<FI, SMEM>(tabs);
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* buf = reinterpret_cast<double*>(f16_smem + PipeSmem<FI, SMEM, 17>::OFF) + warp * (17 * 32);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, n, n < N);
+  for (; n < N; n += stride) {
+    double xu[17], xd[18];
+    pipe_take<17>(buf, lane, xu);
+    pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, n + stride, n + stride < N);
     const int own = owns<FI>(sel, n);
     if (own == 0) continue;
-    double xu[17], xd[18];
-#pragma unroll
-    for (int i = 0; i < 17; i++) xu[i] = xu_g[i * ld_in + n];
     unsigned st = ST_FIDELITY;
     if (own == 1) st = nlplant_eval<FI>(img, xu, sel.xcg ? sel.xcg[n] : sel.xcg_default, xd);
     if (st) {
@@ -74,14 +118,21 @@ calc_xdot_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
                  const double* __restrict__ u_g, long long ld_u, double* __restrict__ xd_g, long long ld_out,
                  long long N, int* __restrict__ status) {
   const double* img = acquire_tables<FI, SMEM>(tabs);
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* buf = reinterpret_cast<double*>(f16_smem + PipeSmem<FI, SMEM, 22>::OFF) + warp * (22 * 32);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, n, n < N);
+  for (; n < N; n += stride) {
+    double xin[22], x[18], u[4], xd[18];
+    pipe_take<22>(buf, lane, xin);
+    pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, n + stride, n + stride < N);
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = xin[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = xin[18 + i];
     const int own = owns<FI>(sel, n);
     if (own == 0) continue;
-    double x[18], u[4], xd[18];
-#pragma unroll
-    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
-#pragma unroll
-    for (int i = 0; i < 4; i++) u[i] = u_g[i * ld_u + n];
     unsigned st = ST_FIDELITY;
     if (own == 1) st = calc_xdot<FI>(img, x, u, sel.xcg ? sel.xcg[n] : sel.xcg_default, xd);
     if (st) {
@@ -560,11 +611,13 @@ cudaError_t launch_nlplant(const LaunchCfg& cfg, const DevTables& tabs, const Ba
   cudaError_t e = cudaSuccess;
   const bool s = cfg.smem_tables;
   if (wants(sel, 1))
-    e = launch_persistent(cfg, s ? nlplant_kernel<1, true> : nlplant_kernel<1, false>, F16_THREADS, table_smem<1>(s), N,
-                          F16_THREADS, tabs, sel, xu, ld_in, xdot, ld_out, N, status);
+    e = launch_persistent(cfg, s ? nlplant_kernel<1, true> : nlplant_kernel<1, false>, F16_THREADS,
+                          s ? PipeSmem<1, true, 17>::TOTAL : PipeSmem<1, false, 17>::TOTAL, N, F16_THREADS, tabs, sel, xu, ld_in,
+                          xdot, ld_out, N, status);
   if (e == cudaSuccess && wants(sel, 0))
-    e = launch_persistent(cfg, s ? nlplant_kernel<0, true> : nlplant_kernel<0, false>, F16_THREADS, table_smem<0>(s), N,
-                          F16_THREADS, tabs, sel, xu, ld_in, xdot, ld_out, N, status);
+    e = launch_persistent(cfg, s ? nlplant_kernel<0, true> : nlplant_kernel<0, false>, F16_THREADS,
+                          s ? PipeSmem<0, true, 17>::TOTAL : PipeSmem<0, false, 17>::TOTAL, N, F16_THREADS, tabs, sel, xu, ld_in,
+                          xdot, ld_out, N, status);
   return e;
 }
 
@@ -576,10 +629,12 @@ cudaError_t launch_calc_xdot(const LaunchCfg& cfg, const DevTables& tabs, const 
   const bool s = cfg.smem_tables;
   if (wants(sel, 1))
     e = launch_persistent(cfg, s ? calc_xdot_kernel<1, true> : calc_xdot_kernel<1, false>, F16_THREADS,
-                          table_smem<1>(s), N, F16_THREADS, tabs, sel, x, ld_x, u, ld_u, xdot, ld_out, N, status);
+                          s ? PipeSmem<1, true, 22>::TOTAL : PipeSmem<1, false, 22>::TOTAL, N, F16_THREADS, tabs, sel, x, ld_x, u,
+                          ld_u, xdot, ld_out, N, status);
   if (e == cudaSuccess && wants(sel, 0))
     e = launch_persistent(cfg, s ? calc_xdot_kernel<0, true> : calc_xdot_kernel<0, false>, F16_THREADS,
-                          table_smem<0>(s), N, F16_THREADS, tabs, sel, x, ld_x, u, ld_u, xdot, ld_out, N, status);
+                          s ? PipeSmem<0, true, 22>::TOTAL : PipeSmem<0, false, 22>::TOTAL, N, F16_THREADS, tabs, sel, x, ld_x, u,
+                          ld_u, xdot, ld_out, N, status);
   return e;
 }
 
