@@ -197,12 +197,17 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
 // ------------------------------------------------------------------------------------------------------
 // linearise_batch: finite-difference A [18x18], B [18x4] of _calc_xdot (env.py:294-342).
 // CTA = 32 aircraft x F16_LIN_WARPS warps, lane = aircraft, so every warp is column-uniform.
-//   phase A  four warps evaluate the stages of f at the unperturbed point (trig | atmos | alpha-beta tables | the other
-//            tables) into shared memory;
-//   phase B  warp w evaluates perturbation columns w, w+W, ...: calc_xdot_col recomputes only the stages the perturbed
-//            component feeds (f16_model.cuh) -- bit-identical to a full evaluation, a third of the work for most columns.
-//            npos / epos (columns 0, 1) feed nothing: those columns of A are exactly zero, as in the reference;
+//   phase A  the stages of f at the unperturbed point go to shared memory: one sin/cos pair per warp (five warps), the
+//            atmosphere, the alpha-beta tables and the other tables (one warp each);
+//   phase B  warp w evaluates perturbation columns w, w+W, ... of columns 2..16: calc_xdot_col recomputes only the stages
+//            the perturbed component feeds (f16_model.cuh) -- bit-identical to a full evaluation.  npos / epos (columns
+//            0, 1) feed nothing: those columns of A are exactly zero, as in the reference; lf1 and the four inputs
+//            (columns 17..21) feed only the actuator rows 12..17, so they skip Nlplant altogether;
 //   phase C  the padded shared tile is written out as contiguous [aircraft][18][18] / [aircraft][18][4] runs.
+// The kernel is latency-bound (8 warps per SM: 255 registers, 105 KB tables + 101 KB tile): measured, 12- and 16-warp
+// variants that keep the stages in shared memory, barrier-free warp-autonomous variants and a cost-balanced column deal all
+// lose to this one through spills into a 28 KB L1 and instruction-cache misses; what paid was fewer passes (actuator-only
+// columns), fewer instructions (div_by) and less code (one evaluation site, calls on the rare paths).
 // ------------------------------------------------------------------------------------------------------
 template <int FI>
 struct LinSmem {
@@ -236,7 +241,7 @@ struct FdQuot {
     rden = 1.0 / den;
     inv_ok = den >= 1e-15 && den <= 1e15;
   }
-  __device__ __forceinline__ double operator()(double num) const { return inv_ok ? div_by(num, den, rden) : num / den; }
+  __device__ __forceinline__ double operator()(double num) const { return inv_ok ? div_by(num, den, rden) : div_plain(num, den); }
 };
 
 // evaluation order, dealt round-robin to the warps (a pass costs about the same whatever it recomputes: measured, a deal
@@ -277,12 +282,19 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
       stat0[lane] = (int)st_base;
     }
     // ---- phase A: the stages of f at the unperturbed point ----
-    if (own == 1 && warp < 4) {
+    if (own == 1 && (warp == 0 || warp >= 4)) {  // one sin/cos pair per warp: alpha | beta, theta (+ tan), phi, psi
+      const int k = warp == 0 ? 0 : warp - 3;
+      const double ang = k == 0 ? xu0[7] : k == 1 ? xu0[8] : k == 2 ? xu0[4] : k == 3 ? xu0[3] : xu0[5];
+      double sn, cs;
+      sincos_pair(ang, sn, cs);
+      stage[(2 * k) * 32 + lane] = sn;  // the field order of XB_TRIG
+      stage[(2 * k + 1) * 32 + lane] = cs;
+#if !F16_FASTPATH
+      if (k == 2) stage[60 * 32 + lane] = tan(xu0[4]);
+#endif
+    } else if (own == 1) {
       XdotBase b;
-      if (warp == 0) {
-        b.tr = trig_eval(xu0);
-        XB_TRIG(XB_ST)
-      } else if (warp == 1) {
+      if (warp == 1) {
         atmos_pair(x0, b.al, b.an);
         XB_ATMOS(XB_ST)
       } else if (!st_base) {
@@ -311,32 +323,24 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
       const int c = c_lin_order[it];
       const int col = c == 22 ? -1 : c;
       const bool reuse_coef = !col_feeds_coef<FI>(col);
-      double x[18], u[4], f[18];
-      XdotBase b;
-#pragma unroll
-      for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? eps : 0.0);
-#pragma unroll
-      for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? eps : 0.0);
-      XB_TRIG(XB_LD) XB_ATMOS(XB_LD)
-      if (reuse_coef) { XB_COEF_AB(XB_LD) XB_COEF_REST(XB_LD) }
-      unsigned st = calc_xdot_col<FI>(img, x, u, xcg, b, col, f);
       double* out = c == 22 ? base + lane * 19 : tile + lane * F16_LIN_TILE_LD + (c < 18 ? c : 324 + (c - 18));
       const int ld = c == 22 ? 1 : (c < 18 ? 18 : 4);
-      if (!st) {
+      unsigned st = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < (scheme != 0 ? 2 : 1) && !st; pass++) {  // one evaluation site: half the code of two
+        const double d = pass ? -eps : eps;
+        double x[18], u[4], f[18];
+        XdotBase b;
 #pragma unroll
-        for (int r = 0; r < 18; r++) out[r * ld] = f[r];  // f(x + eps e_c); central: parked until f(x - eps e_c) is known
-      }
-      if (scheme != 0 && !st) {
+        for (int i = 0; i < 18; i++) x[i] = x0[i] + (i == c ? d : 0.0);
 #pragma unroll
-        for (int i = 0; i < 18; i++) x[i] = x0[i] - (i == c ? eps : 0.0);
-#pragma unroll
-        for (int i = 0; i < 4; i++) u[i] = u0[i] - (i + 18 == c ? eps : 0.0);
+        for (int i = 0; i < 4; i++) u[i] = u0[i] + (i + 18 == c ? d : 0.0);
         XB_TRIG(XB_LD) XB_ATMOS(XB_LD)
         if (reuse_coef) { XB_COEF_AB(XB_LD) XB_COEF_REST(XB_LD) }
         st = calc_xdot_col<FI>(img, x, u, xcg, b, col, f);
         if (!st) {
 #pragma unroll
-          for (int r = 0; r < 18; r++) out[r * ld] = fd(out[r * ld] - f[r]);
+          for (int r = 0; r < 18; r++) out[r * ld] = pass ? fd(out[r * ld] - f[r]) : f[r];  // central: f+ waits in the tile for f-
         }
       }
       if (st) {
