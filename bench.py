@@ -35,6 +35,11 @@ sys.path.insert(0, REPO)
 
 FLOP_PER_STEP = {"open": 750.0, "lqr": 815.0}   # algorithmic FP64 flop per hifi aircraft-step
 BYTES_PER_AIRCRAFT_LAUNCH = 320.0               # read 18 + 4, write 18 doubles, independent of K
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default workload (2^20 aircraft,
+# K = 10000), from the committed `ncu --set full` capture profiles/r01_step_hifi_fast_384_k10000_ncu_summary.md:
+# 194.72 MB read + 107.74 MB written (algorithmic 320 B x 2^20 = 335.5 MB + 4 MB of status words; part of the state was
+# still in L2 from the copy that precedes the launch).  Reported only when the run is that workload.
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 194_723_328 + 107_735_552}
 
 # trim of the reference at 10000 ft / 700 ft/s, xcg 0.25, hifi (tests/golden/env_xcg25.npz, env.py:198-292)
 GOLDEN = os.path.join(REPO, "tests", "golden")
@@ -352,8 +357,10 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": float(peak.value), "unit": "TFLOP/s",
-                "frac": achieved_tf / float(peak.value) if peak.value else None, "traffic": None,
-                "kernel": "step_kernel", "kernel_ms": kernel_ms, "flop_per_aircraft_step": flop,
+                "frac": achieved_tf / float(peak.value) if peak.value else None,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, args.workload, args.math)), "traffic_unit": "bytes per launch (ncu dram read + write)",
+                "kernel": "step_hifi_fast_kernel" if args.math == "fast" else "step_kernel", "kernel_ms": kernel_ms,
+                "flop_per_aircraft_step": flop,
                 "peak_source": "f16_measure_fp64_peak: DFMA micro-benchmark on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"achieved_gbs": n * BYTES_PER_AIRCRAFT_LAUNCH / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
