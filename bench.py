@@ -320,7 +320,8 @@ def run_ours(args):
     from f16_mpc_oop_py_b200 import shard
     dev = f"cuda:{local}" if dist else "cpu"
     elapsed_ms, kernel_ms, e2e_t = shard.max_over_ranks(dist, [elapsed_ms, kernel_ms, e2e_t], dev)
-    summary = shard.gather_summaries(dist, shard.summarise(xf, st), dev)
+    # per-rank statistics reduced on the device (f16_stats.cu), then ONE all-gather of the 74-double rows
+    summary = shard.gather_summaries(dist, f16.state_summary_dev(d_x, n, n, d_st), dev)
     alive = summary["alive_fraction"]
 
     total_steps = float(world) * n * ke * args.steps

@@ -60,7 +60,7 @@ struct State {
   // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
-  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum;
 };
 
 State G;
@@ -215,7 +215,7 @@ void f16_shutdown(void) {
   cudaSetDevice(G.device);
   cudaStreamSynchronize(G.stream);
   for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush, &G.b_l1, &G.b_l2,
-                    &G.b_l3, &G.b_l4, &G.b_l5})
+                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum})
     b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
@@ -601,6 +601,44 @@ int trim_batch(const double* h, const double* V, long long N, double tol, int ma
   if (status) D2H(status, G.b_st.p, n * 4);
   CK(cudaStreamSynchronize(G.stream));
   return F16_OK;
+}
+
+// ---- end-of-run statistics, reduced on the device (f16_stats.cu) ------------------------------------------------------
+static int summary_common(const double* d_x, long long ld, long long N, const int* d_status, double* row_host) {
+  const f16::LaunchCfg c = cfg(false);
+  const int grid = f16::stats::summary_grid(c, N);
+  CK(G.b_sum.reserve(((size_t)grid * 56 + 80) * 8));
+  double* scratch = (double*)G.b_sum.p;
+  double* row = scratch + (size_t)grid * 56;
+  CK(f16::stats::launch_summary(c, d_x, ld, N, d_status, row, scratch, grid));
+  D2H(row_host, row, 74 * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int state_summary_batch_dev(const double* x_soa, long long ld_x, long long N, const int* status, double* row) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !row || (N > 0 && !x_soa) || ld_x < N) { set_err("state_summary_batch_dev: bad argument"); return F16_ERR_ARG; }
+  return summary_common(x_soa, ld_x, N, status, row);
+}
+
+int state_summary_batch(const double* x_soa, long long N, const int* status, double* row) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || !row || (N > 0 && !x_soa)) { set_err("state_summary_batch: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve((n ? 18 * n : 1) * 8));
+  if (n) H2D(G.b_in.p, x_soa, 18 * n * 8);
+  const int* d_st = nullptr;
+  if (status && n) {
+    CK(G.b_st.reserve(n * 4));
+    H2D(G.b_st.p, status, n * 4);
+    d_st = (const int*)G.b_st.p;
+  }
+  return summary_common((const double*)G.b_in.p, N, N, d_st, row);
 }
 
 // ---- between linearise and the LQR law: reduced model, zero-order hold, discrete LQR gain --------------------------------

@@ -71,6 +71,13 @@ cudaError_t launch_dlqr(const LaunchCfg&, const double* Ad, const double* Bd, co
                         long long N, int max_doublings, double tol, double* K, double* P, int* info);
 }  // namespace linalg
 
+// f16_stats.cu: per-state summary of a batch (count, alive, min, max, mean, M2), reduced on the device
+namespace stats {
+cudaError_t launch_summary(const LaunchCfg&, const double* x, long long ld, long long N, const int* status, double* row,
+                           double* scratch, int grid);
+int summary_grid(const LaunchCfg&, long long N);
+}  // namespace stats
+
 // FP64 FMA micro-benchmark (f16_peak.cu): returns flops executed
 cudaError_t launch_dfma_peak(cudaStream_t stream, int sm_count, long long iters, double* sink, double* flops);
 

@@ -105,6 +105,25 @@ def trim(h_t, v_t, fi=1, xcg=0.25, tol=1e-10, maxiter=50000, ux0=None):
     return x, opt
 
 
+def state_summary(x, status=None):
+    """state_summary_batch: the end-of-run statistics of a batch, reduced on the device.  x [18][N], status [N] int32 or
+    None -> the 74-double row [N, alive, min[18], max[18], mean[18], M2[18]] over the aircraft with status 0 (the layout of
+    shard.summarise / shard.merge_summaries: what a rank contributes to the one all-gather of a multi-GPU run)."""
+    x = _c(x)
+    assert x.ndim == 2 and x.shape[0] == 18
+    st = None if status is None else _c(status, np.int32)
+    row = np.empty(74)
+    check(lib.state_summary_batch(_p(x), x.shape[1], _p(st), _p(row)), "state_summary_batch")
+    return row
+
+
+def state_summary_dev(d_x, ld, n, d_status=None):
+    """state_summary_batch_dev on device pointers (plane stride ld): no copy of the state to the host."""
+    row = np.empty(74)
+    check(lib.state_summary_batch_dev(d_x, int(ld), int(n), d_status, _p(row)), "state_summary_batch_dev")
+    return row
+
+
 def reduce_jacobian(A):
     """A [N][18][18] -> (A_na [N][9][9], B_na [N][9][3]): the reduced model of env.py:49,152-193 (an exact gather)."""
     A = _c(A).reshape(-1, 18, 18)
@@ -195,6 +214,10 @@ class F16Batch:
                     xcg=self.xcg if np.ndim(self.xcg) == 0 else 0.25, **kw)
 
     # the driver loops of the reference (test_env.py:452-462, test_env_mk2.py:70-85): K steps, state stored every snap_every
+    def summary(self):
+        """statistics of the current states over the aircraft still flying (status 0), reduced on the device"""
+        return state_summary(self.x, self.status)
+
     def rollout(self, K, snap_every, lqr=None):
         """-> traj [K // snap_every][18][N]; self.x, self.status end as after step(K=K)"""
         ns = int(K) // int(snap_every)

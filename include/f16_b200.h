@@ -151,6 +151,13 @@ int dlqr_batch(const double *Ad, const double *Bd, const double *Q, const double
 int lqr_gain_batch(const double *x_soa, const double *u_soa, long long N, double dt, double *K, const unsigned char *fi,
                    int fi_default, const double *xcg, double xcg_default, int *status);
 
+/* ---- end-of-run statistics, reduced on the device (f16_stats.cu; SURVEY 8e: the row a rank contributes to the one
+ * collective of a run; the reference's drivers keep the whole x_storage on the host instead, test_env.py:452-462) ----
+ * Over the aircraft with status[n] == 0 (all of them if status == NULL):
+ *   row [74] = { N, alive, min[18], max[18], mean[18], M2[18] },  M2 = sum (x - mean)^2  (two passes, no cancellation).
+ * An empty selection gives min = +inf, max = -inf, mean = M2 = 0.  Bit-reproducible for a given device and N. */
+int state_summary_batch(const double *x_soa /* [18][N] */, long long N, const int *status, double *row);
+
 /* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
 int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
                       int fi_default, const double *xcg, double xcg_default, long long N, int *status);
@@ -167,6 +174,9 @@ int linearise_batch_dev(const double *x_soa, long long ld_x, const double *u_soa
 int trim_batch_dev(const double *h, const double *V, long long N, double tol, int maxiter, const double *ux0 /* host */,
                    double *x_trim_soa, long long ld_x, double *info_soa, long long ld_info, const unsigned char *fi,
                    int fi_default, const double *xcg, double xcg_default, int *status);
+
+int state_summary_batch_dev(const double *x_soa, long long ld_x, long long N, const int *status /* device or NULL */,
+                            double *row /* host, 74 doubles */);
 
 int reduce_jacobian_batch_dev(const double *A, long long N, double *A_na, double *B_na);
 int discretise_batch_dev(const double *A, const double *B, int n, int m, long long N, double dt, double *Ad, double *Bd);

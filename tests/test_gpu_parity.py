@@ -691,3 +691,44 @@ def test_step_on_the_envelope_corners(f16, oracle, mode):
     assert ok.sum() > 200
     assert np.all(np.abs(fb.x[:, ok] - ref[:, ok]) <= 1e-13 * np.maximum(np.abs(ref[:, ok]), 1.0))
     assert np.array_equal(fb.x[:, ~ok], x[:, ~ok])      # stopped aircraft keep their state
+
+# ---------------------------------------------------------------------------------------------------------
+# end-of-run statistics reduced on the device (f16_stats.cu)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 257, 100003])
+def test_state_summary_matches_numpy(f16, n):
+    from f16_mpc_oop_py_b200 import shard
+    r = np.random.default_rng(n)
+    g = load_golden("xcg25")
+    x, _ = perturbed_trim(n, g["x_trim"], seed=n, frac=0.05)
+    x[0] = r.uniform(-1e4, 1e4, n)                      # a plane whose mean is far from its spread
+    x[2] = 1e4 + 1e-3 * r.standard_normal(n)            # ... and one where sum-of-squares formulas cancel
+    st = (r.uniform(size=n) < 0.2).astype(np.int32) * 4
+    for status in (None, st):
+        row = f16.state_summary(x, status)
+        ref = shard.summarise(x, np.zeros(n, dtype=np.int32) if status is None else status)
+        assert row[0] == n and row[1] == ref[1]
+        if ref[1] == 0:
+            assert np.all(np.isposinf(row[2:20])) and np.all(np.isneginf(row[20:38])) and not row[38:].any()
+            continue
+        assert np.array_equal(row[2:38], ref[2:38])                                   # min, max: exact
+        assert np.allclose(row[38:56], ref[38:56], rtol=1e-13, atol=1e-13)           # mean
+        assert np.allclose(row[56:74], ref[56:74], rtol=1e-10, atol=1e-18)           # M2 (two passes on both sides)
+    assert np.array_equal(f16.state_summary(x, st), f16.state_summary(x, st))        # fixed reduction tree
+
+
+@pytest.mark.gpu
+def test_state_summary_edges_and_batch_method(f16):
+    row = f16.state_summary(np.zeros((18, 0)))
+    assert row[0] == 0 and row[1] == 0 and np.all(np.isposinf(row[2:20])) and not row[38:].any()
+    g = load_golden("xcg25")
+    x, u = perturbed_trim(2000, g["x_trim"], seed=3, frac=0.05)
+    fb = f16.F16Batch(x, u, xcg=0.25)
+    fb.step(K=50)
+    from f16_mpc_oop_py_b200 import shard
+    ref = shard.summarise(fb.x, fb.status)
+    row = fb.summary()
+    assert row[1] == ref[1] and np.array_equal(row[2:38], ref[2:38]) and np.allclose(row[38:56], ref[38:56], rtol=1e-13)
+    merged = shard.merge_summaries([row])
+    assert merged["alive"] == int(ref[1])
