@@ -78,6 +78,9 @@ def _load():
     L.lqr_gain_batch.argtypes = [c_vp, c_vp, c_ll, ctypes.c_double, c_vp] + sel + [c_vp]
     L.state_summary_batch.argtypes = [c_vp, c_ll, c_vp, c_vp]
     L.state_summary_batch_dev.argtypes = [c_vp, c_ll, c_ll, c_vp, c_vp]
+    L.step_batch_stats.argtypes = [c_vp, c_vp, c_ll, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.POINTER(LqrLaw)] + sel + [c_vp, c_vp]
+    L.step_batch_stats_dev.argtypes = [c_vp, c_ll, c_vp, c_ll, c_ll, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                       ctypes.POINTER(LqrLaw)] + sel + [c_vp, c_vp]
     L.reduce_jacobian_batch_dev.argtypes = [c_vp, c_ll, c_vp, c_vp]
     L.discretise_batch_dev.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, ctypes.c_double, c_vp, c_vp]
     L.dlqr_batch_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, c_vp, c_vp, c_vp]

@@ -604,14 +604,103 @@ int trim_batch(const double* h, const double* V, long long N, double tol, int ma
 }
 
 // ---- end-of-run statistics, reduced on the device (f16_stats.cu) ------------------------------------------------------
+// enqueue the four reduction kernels; row_dev (74 doubles) must not alias the scratch (56 doubles per CTA column)
+static int enqueue_summary(const double* d_x, long long ld, long long N, const int* d_status, double* row_dev, double* scratch,
+                           int grid) {
+  CK(f16::stats::launch_summary(cfg(false), d_x, ld, N, d_status, row_dev, scratch, grid));
+  return F16_OK;
+}
+
 static int summary_common(const double* d_x, long long ld, long long N, const int* d_status, double* row_host) {
-  const f16::LaunchCfg c = cfg(false);
-  const int grid = f16::stats::summary_grid(c, N);
+  const int grid = f16::stats::summary_grid(cfg(false), N);
   CK(G.b_sum.reserve(((size_t)grid * 56 + 80) * 8));
   double* scratch = (double*)G.b_sum.p;
   double* row = scratch + (size_t)grid * 56;
-  CK(f16::stats::launch_summary(c, d_x, ld, N, d_status, row, scratch, grid));
+  int rc = enqueue_summary(d_x, ld, N, d_status, row, scratch, grid);
+  if (rc != F16_OK) return rc;
   D2H(row_host, row, 74 * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+// K steps in chunks of snap_every, one summary row per chunk; x / u / status on the device.  rows_host [K / snap_every][74].
+static int step_stats_core(double* d_x, long long ld_x, const double* d_u, long long ld_u, long long N, int K, int snap_every,
+                           double dt, const f16_lqr_t* lqr, const f16::BatchSel& sel, int* d_status, double* rows_host) {
+  const int n_rows = K / snap_every;
+  const int grid = f16::stats::summary_grid(cfg(false), N);
+  CK(G.b_sum.reserve(((size_t)grid * 56 + (size_t)(n_rows > 0 ? n_rows : 1) * 74 + 8) * 8));
+  double* scratch = (double*)G.b_sum.p;
+  double* rows_dev = scratch + (size_t)grid * 56;
+  const bool smem = G.smem_tables && (N * (long long)snap_every >= 4096);
+  int done = 0, snap = 0;
+  while (done < K) {
+    const int k = (K - done) < snap_every ? (K - done) : snap_every;
+    CK(DISPATCH(launch_step, cfg(smem), tabs(), sel, d_x, ld_x, d_u, ld_u, N, k, dt, reinterpret_cast<const f16::LqrLaw*>(lqr),
+                d_status, nullptr));
+    done += k;
+    if (k == snap_every) {
+      int rc = enqueue_summary(d_x, ld_x, N, d_status, rows_dev + (size_t)snap * 74, scratch, grid);
+      if (rc != F16_OK) return rc;
+      snap++;
+    }
+  }
+  if (n_rows > 0) D2H(rows_host, rows_dev, (size_t)n_rows * 74 * 8);
+  return F16_OK;
+}
+
+static bool lqr_ok(const f16_lqr_t* lqr) {
+  if (!lqr) return true;
+  if (lqr->n_sel < 0 || lqr->n_sel > 18) return false;
+  for (int j = 0; j < lqr->n_sel; j++)
+    if (lqr->sel[j] < 0 || lqr->sel[j] > 17) return false;
+  return true;
+}
+
+int step_batch_stats_dev(double* x_soa, long long ld_x, const double* u_soa, long long ld_u, long long N, int K, int snap_every,
+                         double dt, const f16_lqr_t* lqr, const unsigned char* fi, int fi_default, const double* xcg,
+                         double xcg_default, double* rows, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || K < 0 || snap_every < 1 || (N > 0 && (!x_soa || !u_soa || !status)) || ld_x < N || ld_u < N || !lqr_ok(lqr) ||
+      (!rows && K >= snap_every)) {
+    set_err("step_batch_stats_dev: bad argument");
+    return F16_ERR_ARG;
+  }
+  rc = step_stats_core(x_soa, ld_x, u_soa, ld_u, N, K, snap_every, dt, lqr, sel_of(fi, fi_default, xcg, xcg_default), status, rows);
+  if (rc != F16_OK) return rc;
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
+int step_batch_stats(double* x_soa, const double* u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t* lqr,
+                     const unsigned char* fi, int fi_default, const double* xcg, double xcg_default, double* rows, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N < 0 || K < 0 || snap_every < 1 || (N > 0 && (!x_soa || !u_soa)) || !lqr_ok(lqr) || (!rows && K >= snap_every)) {
+    set_err("step_batch_stats: bad argument");
+    return F16_ERR_ARG;
+  }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve((n ? 18 * n : 1) * 8));
+  CK(G.b_in2.reserve((n ? 4 * n : 1) * 8));
+  CK(G.b_st.reserve((n ? n : 1) * 4));
+  const unsigned char* d_fi = nullptr;
+  const double* d_xcg = nullptr;
+  if (n) {
+    if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
+    H2D(G.b_in.p, x_soa, 18 * n * 8);
+    H2D(G.b_in2.p, u_soa, 4 * n * 8);
+    CK(cudaMemsetAsync(G.b_st.p, 0, n * 4, G.stream));
+  }
+  rc = step_stats_core((double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, K, snap_every, dt, lqr,
+                       sel_of(d_fi, fi_default, d_xcg, xcg_default), (int*)G.b_st.p, rows);
+  if (rc != F16_OK) return rc;
+  if (n) {
+    D2H(x_soa, G.b_in.p, 18 * n * 8);
+    if (status) D2H(status, G.b_st.p, n * 4);
+  }
   CK(cudaStreamSynchronize(G.stream));
   return F16_OK;
 }

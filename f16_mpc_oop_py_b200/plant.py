@@ -218,6 +218,15 @@ class F16Batch:
         """statistics of the current states over the aircraft still flying (status 0), reduced on the device"""
         return state_summary(self.x, self.status)
 
+    def rollout_stats(self, K, snap_every, lqr=None):
+        """Monte-Carlo rollout that keeps statistics instead of trajectories: -> rows [K // snap_every][74] (state_summary
+        layout) of the batch after every snap_every steps; self.x, self.status end as after step(K=K)"""
+        rows = np.empty((int(K) // int(snap_every), 74))
+        law = ctypes.byref(lqr) if lqr is not None else None
+        check(lib.step_batch_stats(_p(self.x), _p(self.u), self.n, int(K), int(snap_every), float(self.dt), law, *self._sel_c(),
+                                   _p(rows), _p(self.status)), "step_batch_stats")
+        return rows
+
     def rollout(self, K, snap_every, lqr=None):
         """-> traj [K // snap_every][18][N]; self.x, self.status end as after step(K=K)"""
         ns = int(K) // int(snap_every)

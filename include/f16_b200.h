@@ -157,6 +157,11 @@ int lqr_gain_batch(const double *x_soa, const double *u_soa, long long N, double
  *   row [74] = { N, alive, min[18], max[18], mean[18], M2[18] },  M2 = sum (x - mean)^2  (two passes, no cancellation).
  * An empty selection gives min = +inf, max = -inf, mean = M2 = 0.  Bit-reproducible for a given device and N. */
 int state_summary_batch(const double *x_soa /* [18][N] */, long long N, const int *status, double *row);
+/* A Monte-Carlo rollout that keeps statistics instead of trajectories (BASELINE cfg 5: 64 Mi aircraft -- x_storage of
+ * test_env.py:452-462 would be 9 GB per snapshot): K steps as step_batch, and after every snap_every steps the summary row of
+ * the whole batch -> rows [K / snap_every][74].  States and status words end bit-identical to one step_batch call of K steps. */
+int step_batch_stats(double *x_soa, const double *u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t *lqr,
+                     const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, double *rows, int *status);
 
 /* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
 int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
@@ -177,6 +182,9 @@ int trim_batch_dev(const double *h, const double *V, long long N, double tol, in
 
 int state_summary_batch_dev(const double *x_soa, long long ld_x, long long N, const int *status /* device or NULL */,
                             double *row /* host, 74 doubles */);
+int step_batch_stats_dev(double *x_soa, long long ld_x, const double *u_soa, long long ld_u, long long N, int K, int snap_every,
+                         double dt, const f16_lqr_t *lqr /* host */, const unsigned char *fi, int fi_default, const double *xcg,
+                         double xcg_default, double *rows /* host, [K / snap_every][74] */, int *status /* device, required */);
 
 int reduce_jacobian_batch_dev(const double *A, long long N, double *A_na, double *B_na);
 int discretise_batch_dev(const double *A, const double *B, int n, int m, long long N, double dt, double *Ad, double *Bd);

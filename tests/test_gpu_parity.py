@@ -732,3 +732,23 @@ def test_state_summary_edges_and_batch_method(f16):
     assert row[1] == ref[1] and np.array_equal(row[2:38], ref[2:38]) and np.allclose(row[38:56], ref[38:56], rtol=1e-13)
     merged = shard.merge_summaries([row])
     assert merged["alive"] == int(ref[1])
+
+@pytest.mark.gpu
+def test_rollout_stats_equals_chunked_steps_and_summaries(f16, mode):
+    """step_batch_stats: statistics every M steps without trajectories = step(M) + summary(), repeated, bit for bit"""
+    g = load_golden("xcg35")
+    n, K, M = 3000, 240, 40
+    x, u = perturbed_trim(n, g["x_trim"], seed=12, frac=0.05)
+    x[7, :40] = np.deg2rad(44.9)                      # near the edge of the tables
+    x[7, 40:60] = np.deg2rad(46.0)                    # outside them: frozen from the first step, not in the statistics
+    a = f16.F16Batch(x, u, xcg=0.35)
+    rows = a.rollout_stats(K, M)
+    assert rows.shape == (K // M, 74)
+    b = f16.F16Batch(x, u, xcg=0.35)
+    for i in range(K // M):
+        b.step(K=M)
+        assert np.array_equal(rows[i], b.summary(), equal_nan=True), i
+    assert np.array_equal(a.x, b.x, equal_nan=True) and np.array_equal(a.status, b.status)
+    assert rows[0][0] == n and rows[-1][1] == (b.status == 0).sum() and 0 < rows[-1][1] < n
+    assert np.all(np.diff(rows[:, 1]) <= 0)           # survivors never come back
+
