@@ -86,7 +86,7 @@ void f16_nlplant_xcg(const double *xu, double *xdot, int fidelity, double xcg);
 void f16_atmos(double alt, double vt, double *coeff);
 
 /* ---- library state --------------------------------------------------------------------------------- */
-/* Idempotent.  table_path: the packed blob (f16_aero_v1.bin), or a directory holding the reference's C/*.dat
+/* Idempotent.  table_path: the packed blob (f16_aero_v1.bin), or a directory holding the reference's C/<table>.dat
  * files, or NULL to search $F16_TABLE_PATH, <lib dir>/../data/f16_aero_v1.bin, ./C/.  device: CUDA ordinal,
  * or -1 for $F16_DEVICE / $LOCAL_RANK / 0.  Called implicitly (NULL, -1) by every other entry point. */
 int f16_init(const char *table_path, int device);

@@ -89,3 +89,32 @@ def test_package_never_touches_the_oracle():
                 txt = open(os.path.join(root, fn)).read()
                 assert "f16_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "hostemu" not in txt or fn == "f16_model.cuh", fn
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "cfg1_open_loop")
+    pkg = os.path.join(REPO, "f16_mpc_oop_py_b200")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(REPO, "include"),
+                    os.path.join(REPO, "examples", "cfg1_open_loop.c"), "-o", exe, "-L" + pkg, "-lf16_b200",
+                    "-Wl,-rpath," + pkg, "-lm"], check=True)
+    return exe
+
+
+def test_c_host_program_builds_against_the_header(tmp_path):
+    """host code in plain C over include/f16_b200.h (the header must be C, not C++); without a B200 it reports and exits 2"""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_program_runs_cfg1(tmp_path):
+    """BASELINE cfg 1 from C: trim_batch -> linearise_batch -> one step_batch call of 10000 steps, checked against the
+    reference's 10 s trajectory (SURVEY 8c known answer 3) inside the program"""
+    import subprocess
+    r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "matches the reference's 10 s trajectory" in r.stdout
