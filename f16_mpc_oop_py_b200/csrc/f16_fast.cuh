@@ -485,9 +485,203 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The lofi (Stevens-Lewis) model on the same arithmetic: env.py::_calc_xdot with fi_flag = 0.  `img` is the 7 KB lofi
+// step image: the lofi tables of f16_tables.h (F16_LOFI_*, 792 doubles) followed by the 48 x 2 centre table of
+// half_rho().  Look-ups as lofi_F16_AeroData.c:12-368 (5-degree alpha grid with linear extrapolation, |beta| grid 0:5:30,
+// elevator grid -24:12:24), totals as nlplant.c:258-286,333-377 with every leading-edge-flap term zero (:256,295-319).
+// alpha is not confined to the hifi tables here, so it takes the reduced sincos like the Euler angles.
+// ------------------------------------------------------------------------------------------------------
+#define F16_LOFI_STEP_IMG_DOUBLES (F16_IMG_LOFI_DOUBLES + 2 * F16_FI_NPOW)
+
+struct LofiA {
+  int k, L;    // zero-based columns of the two alpha neighbours
+  double ada;  // |alpha / 5 - k|
+};
+F16_FD double lrow(const double* row, const LofiA& A) {
+  const double lo = row[A.k];
+  return fma(A.ada, row[A.L] - lo, lo);
+}
+
+template <bool LIBM_TRIG>
+F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
+  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
+  const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
+  if (!(fabs(beta) <= 30.0)) return false;  // lofi_envelope(): dmomdcon indexes past its arrays beyond 30 deg
+
+  double sa, ca, sb, cb, st, ct, sphi, cphi, spsi, cpsi;
+  sincos_quarter(x[8], sb, cb);
+  if (LIBM_TRIG) {
+    sincos_libm(x[7], &sa, &ca);
+    sincos_libm(x[4], &st, &ct);
+    sincos_libm(x[3], &sphi, &cphi);
+    sincos_libm(x[5], &spsi, &cpsi);
+  } else {
+    double r7, r4, r3, r5;
+    const int q7 = reduce_pio2(x[7], r7), q4 = reduce_pio2(x[4], r4), q3 = reduce_pio2(x[3], r3), q5 = reduce_pio2(x[5], r5);
+    sincos_quarter(r7, sa, ca);
+    sincos_quarter(r4, st, ct);
+    sincos_quarter(r3, sphi, cphi);
+    sincos_quarter(r5, spsi, cpsi);
+    if (((q7 | q4 | q3 | q5) & 3) != 0) {
+      quadrant_fix(q7, sa, ca);
+      quadrant_fix(q4, st, ct);
+      quadrant_fix(q3, sphi, cphi);
+      quadrant_fix(q5, spsi, cpsi);
+    }
+  }
+
+  double vt = x[6];
+  if (vt <= 0.01) vt = 0.01;  // nlplant.c:104
+  const double P = x[9], Q = x[10], R = x[11], T = x[12];
+  const double tfac = fma(K.tlapse, x[2], 1.0);
+  const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
+  const double qbar = half_rho(img + F16_IMG_LOFI_DOUBLES - F16_FI_POW, tfac) * (vt * vt);
+  const double vc = vt * cb, tc = ct * temp;
+  const double rr = rcp_nr(vc * tc);
+  const double inv_vc = rr * tc, inv_tc = rr * vc;
+  const double inv_vt = inv_vc * cb, inv_ct = inv_tc * temp, inv_temp = inv_tc * ct;
+  const double dail = x[14] * K.inv21_5, drud = x[15] * K.inv30;
+
+  // navigation + kinematics, nlplant.c:148-176
+  const double U = vc * ca, V = vt * sb, W = vc * sa;
+  {
+    const double sphi_cpsi = sphi * cpsi, cphi_spsi = cphi * spsi, sphi_spsi = sphi * spsi, cphi_cpsi = cphi * cpsi,
+                 cphi_st = cphi * st;
+    xd[0] = fma(U, ct * cpsi, fma(V, fma(sphi_cpsi, st, -cphi_spsi), W * fma(cphi_st, cpsi, sphi_spsi)));
+    xd[1] = fma(U, ct * spsi, fma(V, fma(sphi_spsi, st, cphi_cpsi), W * fma(cphi_st, spsi, -sphi_cpsi)));
+    xd[2] = fma(U, st, -fma(V, sphi * ct, W * (cphi * ct)));
+  }
+  const double qr = fma(Q, sphi, R * cphi);
+  xd[3] = fma(st * inv_ct, qr, P);
+  xd[4] = fma(Q, cphi, -(R * sphi));
+  xd[5] = qr * inv_ct;
+  const double qQ = K.half_cbar * inv_vt * Q, bR = (0.5 * B) * inv_vt * R, bP = (0.5 * B) * inv_vt * P;
+
+  // ---- look-ups ----
+  LofiA A;
+  {
+    const double s = 0.2 * alpha;  // lofi:31-45
+    int k = (int)s;                // fix(): truncation toward zero
+    k = k <= -2 ? -1 : (k >= 9 ? 8 : k);
+    const double da = s - (double)k;
+    A.L = k + ((da > 0) - (da < 0)) + 2;
+    A.k = k + 2;
+    A.ada = fabs(da);
+  }
+  const double ab = 0.2 * fabs(beta);
+  const int mb = (int)ab;  // 0..6
+  double Cl_tot, Cn_tot;
+  {  // dmomdcon (lofi:59-183): rows m, m + 1 of ALA, ALR, ANA, ANR
+    const int m = mb >= 7 ? 6 : mb;
+    const double db = ab - (double)m;
+    double r[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int t = 0; t < 4; t++) {
+      const double* Tt = img + F16_LOFI_DMOM + t * 96 + m * 12;
+      const double v = lrow(Tt, A);
+      r[t] = fma(db, lrow(Tt + 12, A) - v, v);
+    }
+    Cl_tot = fma(r[1], drud, r[0] * dail);  // dCl_a20 dail + dCl_r30 drud, nlplant.c:270-273,370-377
+    Cn_tot = fma(r[3], drud, r[2] * dail);
+  }
+  {  // clcn (lofi:185-262), odd in beta
+    const int m = mb == 0 ? 1 : (mb >= 6 ? 5 : mb);
+    const double db = ab - (double)m;
+    const int n = m + ((db > 0) - (db < 0));
+    const double adb = fabs(db);
+    const double* TL = img + F16_LOFI_CLCN;
+    const double* TN = TL + 84;
+    double v = lrow(TL + m * 12, A);
+    const double cl = fma(adb, lrow(TL + n * 12, A) - v, v);
+    v = lrow(TN + m * 12, A);
+    const double cn = fma(adb, lrow(TN + n * 12, A) - v, v);
+    const bool neg = beta < 0.0, zero = beta == 0.0;
+    Cl_tot += zero ? 0.0 : (neg ? -cl : cl);
+    Cn_tot += zero ? 0.0 : (neg ? -cn : cn);
+  }
+  double Cx_tot, Cm_tot;
+  {  // cxcm (lofi:265-336)
+    const double s = el * (1.0 / 12.0);
+    int m = (int)s;
+    m = m <= -2 ? -1 : (m >= 2 ? 1 : m);
+    const double de = s - (double)m;
+    const int n = m + ((de > 0) - (de < 0)) + 2;
+    m += 2;
+    const double ade = fabs(de);
+    const double* TX = img + F16_LOFI_CXCM;
+    const double* TM = TX + 60;
+    double v = lrow(TX + m * 12, A);
+    Cx_tot = fma(ade, lrow(TX + n * 12, A) - v, v);
+    v = lrow(TM + m * 12, A);
+    Cm_tot = fma(ade, lrow(TM + n * 12, A) - v, v);
+  }
+  // cz (lofi:339-368) and Cy (nlplant.c:283)
+  const double b573 = beta * (1.0 / 57.3);
+  double Cz_tot = fma(lrow(img + F16_LOFI_CZ, A), fma(-b573, b573, 1.0), -(0.19 / 25.0) * el);
+  double Cy_tot = fma(0.086, drud, fma(0.021, dail, -0.02 * beta));
+  {  // damping (lofi:12-56), nlplant.c:333-377 with dlef = 0
+    const double* D = img + F16_LOFI_DAMP;
+    Cx_tot = fma(qQ, lrow(D + 0 * 12, A), Cx_tot);
+    Cz_tot = fma(qQ, lrow(D + 3 * 12, A), Cz_tot);
+    Cm_tot = fma(qQ, lrow(D + 6 * 12, A), Cm_tot);
+    Cm_tot = fma(Cz_tot, xcgr - xcg, Cm_tot);
+    Cy_tot = fma(bR, lrow(D + 1 * 12, A), Cy_tot);
+    Cy_tot = fma(bP, lrow(D + 2 * 12, A), Cy_tot);
+    Cn_tot = fma(bR, lrow(D + 7 * 12, A), Cn_tot);
+    Cn_tot = fma(bP, lrow(D + 8 * 12, A), Cn_tot);
+    Cn_tot = fma(Cy_tot, (xcg - xcgr) * K.xcg_arm, Cn_tot);
+    Cl_tot = fma(bR, lrow(D + 4 * 12, A), Cl_tot);
+    Cl_tot = fma(bP, lrow(D + 5 * 12, A), Cl_tot);
+  }
+
+  // body-axis accelerations, nlplant.c:383-387
+  const double qS_m = qbar * K.S_m;
+  const double gct = K.g * ct;
+  const double Udot = fma(T, K.inv_m, fma(qS_m, Cx_tot, fma(-K.g, st, fma(R, V, -(Q * W)))));
+  const double Vdot = fma(qS_m, Cy_tot, fma(gct, sphi, fma(P, W, -(R * U))));
+  const double Wdot = fma(qS_m, Cz_tot, fma(gct, cphi, fma(Q, U, -(P * V))));
+  const double vtd = fma(ca * cb, Udot, fma(sb, Vdot, (sa * cb) * Wdot));
+  xd[6] = vtd;
+  xd[7] = fma(ca, Wdot, -(sa * Udot)) * inv_vc;
+  xd[8] = fma(-sb, vtd, Vdot) * inv_vc;
+
+  // moments, nlplant.c:413-436 (Heng = 0)
+  const double qSb = qbar * (S * B);
+  const double L_tot = Cl_tot * qSb, N_tot = Cn_tot * qSb, M_tot = Cm_tot * (qbar * (S * cbar));
+  const double PQ = P * Q, QR = Q * R;
+  xd[9] = fma(K.ixx_l, L_tot, fma(K.ixx_n, N_tot, fma(K.ixx_qr, QR, K.ixx_pq * PQ)));
+  xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * fma(P, P, -(R * R))));
+  xd[11] = fma(K.izz_n, N_tot, fma(K.izz_l, L_tot, fma(K.izz_pq, PQ, K.izz_qr * QR)));
+
+  // actuators and leading-edge flap, utils.py:289-330 (the flap states evolve in the lofi model too; Nlplant ignores them)
+  const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
+  const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
+  const double lf_in = fma(2.0, alpha_deg, x[17]);
+  const double lef_cmd = clipd(fma(lf_in, K.c1_38, K.c1_45) - atmos_out, 0, 25);
+  const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
+               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_cmd - x[16]);
+  xd[12] = r12;
+  xd[13] = r13;
+  xd[14] = r14;
+  xd[15] = r15;
+  xd[16] = r16;
+  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
+    xd[12] = clipd(r12, -10000, 10000);
+    xd[13] = clipd(r13, -60, 60);
+    xd[14] = clipd(r14, -80, 80);
+    xd[15] = clipd(r15, -120, 120);
+    xd[16] = clipd(r16, -25, 25);
+  }
+  xd[17] = (alpha_deg - lf_in) * 7.25;
+  return true;
+}
+
 // K fused Euler steps of env.py::step from step k; stops (k < K on return) at the first state that fails step_ok or
 // leaves the tables.  The state is not advanced on the failing step.
-template <bool LQR, bool LIBM_TRIG>
+template <bool LQR, bool LIBM_TRIG, int FI = 1>
 F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg, double dt,
                      int k, int K) {
   double uc[4];
@@ -503,7 +697,7 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
       lqr_action_dense(*lqr, x, u_in, u);
       clip_commands(u, uc);
     }
-    if (!calc_xdot_hifi<LIBM_TRIG>(img, x, uc, xcg, xd)) break;
+    if (!(FI ? calc_xdot_hifi<LIBM_TRIG>(img, x, uc, xcg, xd) : calc_xdot_lofi<LIBM_TRIG>(img, x, uc, xcg, xd))) break;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -512,25 +706,27 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
   return k;
 }
 
+template <int FI = 1>
 F16_FD unsigned exact_status(const double (&x)[18], const double (&u_in)[4]) {
   unsigned st = step_bounds(x, u_in);
-  if (!st) st = hifi_envelope(x[7] * (180.0 / 3.141592653589793), x[8] * (180.0 / 3.141592653589793), x[13]);
+  const double a = x[7] * (180.0 / 3.141592653589793), b = x[8] * (180.0 / 3.141592653589793);
+  if (!st) st = FI ? hifi_envelope(a, b, x[13]) : lofi_envelope(a, b, x[13]);
   return st;
 }
 
 // the whole step_batch semantics for one aircraft: returns the status word, k = steps taken
-template <bool LQR>
+template <bool LQR, int FI = 1>
 F16_FD unsigned step_aircraft(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg,
                               double dt, int K, int& k) {
   k = 0;
   if (either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3])) return K > 0 ? step_bounds(x, u_in) : 0u;
-  k = run_steps<LQR, false>(img, x, u_in, lqr, xcg, dt, 0, K);
+  k = run_steps<LQR, false, FI>(img, x, u_in, lqr, xcg, dt, 0, K);
   if (k == K) return 0u;
-  unsigned st = exact_status(x, u_in);  // stopped early: the exact status word of the frozen state
+  unsigned st = exact_status<FI>(x, u_in);  // stopped early: the exact status word of the frozen state
   if (st) return st;
   // none of the reference's stop conditions: an Euler angle beyond 2^30 rad -- carry on with libm's trig
-  k = run_steps<LQR, true>(img, x, u_in, lqr, xcg, dt, k, K);
-  return k == K ? 0u : exact_status(x, u_in);
+  k = run_steps<LQR, true, FI>(img, x, u_in, lqr, xcg, dt, k, K);
+  return k == K ? 0u : exact_status<FI>(x, u_in);
 }
 
 }  // namespace fastmath

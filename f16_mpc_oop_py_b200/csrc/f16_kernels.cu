@@ -674,6 +674,10 @@ cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const Batch
       e = launch_step_hifi_fast(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, status, steps_done);
       continue;
     }
+    if (FI == 0) {  // ... and so does the lofi step
+      e = launch_step_lofi_fast(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, status, steps_done);
+      continue;
+    }
 #endif
     StepKern k = FI ? (lqr_host ? pick_step<1, true>(cfg.smem_tables, threads) : pick_step<1, false>(cfg.smem_tables, threads))
                     : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));

@@ -53,6 +53,36 @@ step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// step_batch, lofi, F16_MATH_FAST: the Stevens-Lewis model on the same arithmetic (fastmath::calc_xdot_lofi).  Its step
+// image is 7 KB (lofi tables + the centre table of half_rho), copied into shared memory by the CTA itself.
+// ------------------------------------------------------------------------------------------------------
+template <bool LQR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+step_lofi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
+                      const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
+                      int* __restrict__ status, int* __restrict__ steps_done) {
+  double* img = reinterpret_cast<double*>(f16_smem);
+  for (int i = threadIdx.x; i < F16_LOFI_STEP_IMG_DOUBLES; i += THREADS)
+    img[i] = i < F16_IMG_LOFI_DOUBLES ? tabs.lofi[i] : tabs.hifi_fast[F16_FI_POW + (i - F16_IMG_LOFI_DOUBLES)];
+  __syncthreads();
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    if (owns<0>(sel, n) == 0) continue;  // fidelity flags other than 0 / 1 are reported by the hifi kernel
+    double x[18], u_in[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_g[i * ld_x + n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
+    const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+    int k;
+    const unsigned st = fastmath::step_aircraft<LQR, 0>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (status) status[n] = (int)st;
+    if (steps_done) steps_done[n] = k;
+  }
+}
+
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*);
 
@@ -83,6 +113,24 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   StepKern k = lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads);
   const int smem = cfg.smem_tables ? FAST_SMEM_BYTES : 0;
   return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+}
+
+// the caller (launch_step) has uploaded nothing yet for the law: same symbol, same protocol as above
+cudaError_t launch_step_lofi_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x,
+                                  const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
+                                  int* status, int* steps_done) {
+  if (N <= 0) return cudaSuccess;
+  if (lqr_host) {
+    static fastmath::LqrDense dense;
+    cudaError_t e = cudaStreamSynchronize(cfg.stream);
+    if (e != cudaSuccess) return e;
+    fastmath::make_dense_law(*lqr_host, dense);
+    e = cudaMemcpyToSymbolAsync(c_lqr_fast, &dense, sizeof(dense), 0, cudaMemcpyHostToDevice, cfg.stream);
+    if (e != cudaSuccess) return e;
+  }
+  const int smem = F16_LOFI_STEP_IMG_DOUBLES * 8;
+  StepKern k = lqr_host ? step_lofi_fast_kernel<true, 384> : step_lofi_fast_kernel<false, 384>;
+  return launch_persistent(cfg, k, 384, smem, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
 }
 
 }  // namespace fast

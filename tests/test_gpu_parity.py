@@ -399,6 +399,53 @@ def test_closed_loop_lqr_fused(f16, oracle, mode):
     assert scaled_err(fb.x[:, alive], ref[:, alive]) < TOL_TRAJ
 
 
+def test_lofi_step_over_the_whole_lofi_envelope(f16, oracle, mode):
+    """the lofi step (its own kernel on the fast arithmetic in F16_MATH_FAST) from states anywhere in the lofi envelope --
+    alpha -20..89 deg (linear extrapolation of the 5-degree grid beyond -10..45), beta to +-29.9 deg either sign, every
+    elevator cell, both xcg -- open loop and with a fused feedback law; short horizon so that nobody leaves on the way"""
+    from _inputs import random_envelope_xu
+    n = 4096
+    xu = random_envelope_xu(n, seed=41, hifi=False)
+    r = np.random.default_rng(42)
+    x = np.vstack([xu, r.uniform(-20, 5, (1, n))])          # lf1
+    x[2] = r.uniform(1000, 39000, n)
+    x[7, :8] = np.deg2rad([-20.0, -10.0, 0.0, 45.0, 60.0, 89.0, 5.0, -5.0])      # grid nodes and ends
+    x[8, 8:14] = np.deg2rad([0.0, 5.0, -5.0, 29.9, -29.9, 15.0])
+    x[13, 14:20] = [-25.0, -24.0, -12.0, 0.0, 12.0, 25.0]
+    u = np.vstack([r.uniform(1000, 19000, n), r.uniform(-25, 25, n), r.uniform(-21.5, 21.5, n), r.uniform(-30, 30, n)])
+    g = load_golden("lofi_xcg25")
+    sel = list(g["mpc_x_idx"])
+    K = np.zeros((3, 9))
+    K[0, [2, 5]] = [-3.0, -0.8]
+    K[1, [0, 4]] = [-0.3, -0.15]
+    K[2, [3, 6]] = [0.2, -0.1]
+    for xcg in (0.25, 0.35):
+        for law, olaw in ((None, None), (f16.make_lqr(K, sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3]),
+                                         orc_make_lqr(K, sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3]))):
+            ref, rst = oracle.step_batch(x, u, 50, 0.001, 0, xcg, olaw, checker(oracle))
+            fb = f16.F16Batch(x, u, fi_flag=0, xcg=xcg)
+            fb.step(K=50, lqr=law)
+            alive = (rst == 0) & (fb.status == 0)
+            assert alive.mean() > 0.9 and np.mean(rst != fb.status) < 0.005
+            assert scaled_err(fb.x[:, alive], ref[:, alive]) < TOL_TRAJ
+
+
+def test_step_mixed_fidelity_batch_equals_separate_batches(f16, mode):
+    """BASELINE cfg 3 as a step: per-aircraft fidelity flags and xcg in ONE call = the hifi and lofi batches run apart"""
+    g = load_golden("xcg25")
+    n = 1500
+    x, u = perturbed_trim(n, g["x_trim"], seed=77, frac=0.04)
+    fi = (np.arange(n) % 3 != 0).astype(np.uint8)
+    xcg = np.where(np.arange(n) % 2 == 0, 0.25, 0.35)
+    mixed = f16.F16Batch(x, u, fi_flag=fi, xcg=xcg)
+    mixed.step(K=300)
+    for f in (0, 1):
+        m = fi == f
+        part = f16.F16Batch(x[:, m], u[:, m], fi_flag=f, xcg=xcg[m])
+        part.step(K=300)
+        assert np.array_equal(mixed.x[:, m], part.x, equal_nan=True) and np.array_equal(mixed.status[m], part.status)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # linearise_batch (env.py:294-342; BASELINE cfg 4)
 # ---------------------------------------------------------------------------------------------------------
