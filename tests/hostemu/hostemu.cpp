@@ -108,6 +108,27 @@ __attribute__((visibility("default"))) unsigned emu_step_fast(double* x_, const 
   return st;
 }
 
+// the lofi step on the same arithmetic (step_lofi_fast_kernel): its image is the lofi tables + the centre table of half_rho
+__attribute__((visibility("default"))) unsigned emu_step_fast_lofi(double* x_, const double* u_, int K, double dt, double xcg,
+                                                                   const f16::LqrLaw* lqr, int* steps_done) {
+  static std::vector<double> img;
+  if (img.empty()) {
+    img = g_lofi;
+    img.insert(img.end(), g_fast.begin() + F16_FI_POW, g_fast.begin() + F16_FI_POW + 2 * F16_FI_NPOW);
+  }
+  double x[18], u_in[4];
+  for (int i = 0; i < 18; i++) x[i] = x_[i];
+  for (int i = 0; i < 4; i++) u_in[i] = u_[i];
+  int k = 0;
+  f16::fastmath::LqrDense dense;
+  if (lqr) f16::fastmath::make_dense_law(*lqr, dense);
+  const unsigned st = lqr ? f16::fastmath::step_aircraft<true, 0>(img.data(), x, u_in, &dense, xcg, dt, K, k)
+                          : f16::fastmath::step_aircraft<false, 0>(img.data(), x, u_in, nullptr, xcg, dt, K, k);
+  for (int i = 0; i < 18; i++) x_[i] = x[i];
+  if (steps_done) *steps_done = k;
+  return st;
+}
+
 // accuracy probes of the fast elementary functions: out = {sin, cos (sincos_any), sin, cos (sincos_quarter), half_rho}
 __attribute__((visibility("default"))) void emu_fastmath_probe(double x, double tfac, double* out) {
   f16::fastmath::sincos_any(x, out[0], out[1]);

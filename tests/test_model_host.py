@@ -140,6 +140,7 @@ def emu_fast(emu):
     emu.emu_step_fast.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(LqrLaw),
                                   ctypes.POINTER(ctypes.c_int)]
     emu.emu_fastmath_probe.argtypes = [ctypes.c_double, ctypes.c_double, dp]
+    emu.emu_step_fast_lofi.argtypes = emu.emu_step_fast.argtypes
     return emu
 
 
@@ -365,3 +366,40 @@ def test_fast_calc_xdot_on_the_envelope_corners(emu_fast, oracle):
     ok = st == 0
     assert ok.sum() > 200
     assert scaled_err(out[:, ok], ref[:, ok]) < 1e-12
+
+def test_fast_lofi_step_over_the_lofi_envelope(emu_fast, oracle):
+    """fastmath::calc_xdot_lofi (the F16_MATH_FAST lofi step) against the oracle: alpha -20..89 deg incl. the grid nodes and
+    the extrapolated ends, beta of either sign to +-29.9 deg and exactly 0, every elevator cell, both xcg, open loop and
+    with a feedback law; statuses equal"""
+    from _inputs import random_envelope_xu
+    from conftest import scaled_err
+    n = 300
+    xu = random_envelope_xu(n, seed=41, hifi=False)
+    r = np.random.default_rng(42)
+    x0 = np.vstack([xu, r.uniform(-20, 5, (1, n))])
+    x0[2] = r.uniform(1000, 39000, n)
+    x0[7, :8] = np.deg2rad([-20.0, -10.0, 0.0, 45.0, 60.0, 89.0, 5.0, -5.0])
+    x0[8, 8:14] = np.deg2rad([0.0, 5.0, -5.0, 29.9, -29.9, 15.0])
+    x0[13, 14:20] = [-25.0, -24.0, -12.0, 0.0, 12.0, 25.0]
+    x0[8, 20] = np.deg2rad(30.5)                       # outside: frozen at once with the oracle's status word
+    u0 = np.vstack([r.uniform(1000, 19000, n), r.uniform(-25, 25, n), r.uniform(-21.5, 21.5, n), r.uniform(-30, 30, n)])
+    g = load_golden("lofi_xcg25")
+    sel = list(g["mpc_x_idx"])
+    K = np.zeros((3, 9))
+    K[0, [2, 5]] = [-3.0, -0.8]
+    K[1, [0, 4]] = [-0.3, -0.15]
+    law = make_lqr(K, sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+    for xcg in (0.25, 0.35):
+        for lw in (None, law):
+            ref, st = oracle.step_batch(x0.copy(), u0.copy(), 40, 0.001, 0, xcg, lw, PORT)
+            out = np.empty_like(x0)
+            sts = np.zeros(n, dtype=np.int64)
+            for i in range(n):
+                x = np.ascontiguousarray(x0[:, i])
+                sts[i] = emu_fast.emu_step_fast_lofi(_p(x), _p(np.ascontiguousarray(u0[:, i])), 40, 0.001, xcg,
+                                                     ctypes.byref(lw) if lw is not None else None, None)
+                out[:, i] = x
+            assert np.mean(sts != st) < 0.01 and sts[20] == st[20] != 0
+            alive = (st == 0) & (sts == 0)
+            assert alive.mean() > 0.9
+            assert scaled_err(out[:, alive], ref[:, alive]) < 1e-10
