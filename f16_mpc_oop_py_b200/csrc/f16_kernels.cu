@@ -720,6 +720,14 @@ cudaError_t launch_trim(const LaunchCfg& cfg, const DevTables& tabs, const Batch
   for (int k = 0; k < 5; k++) g.ux[k] = ux0[k];
   cudaError_t e = cudaSuccess;
   const bool s = cfg.smem_tables;
+#if defined(F16_FAST)
+  if (s) {  // the objective on the step kernel's arithmetic (f16_step_fast.cu)
+    if (wants(sel, 1)) e = launch_trim_fast(cfg, tabs, sel, 1, h, v, N, tol, maxiter, ux0, x_trim, ld_x, info, ld_info, status);
+    if (e == cudaSuccess && wants(sel, 0))
+      e = launch_trim_fast(cfg, tabs, sel, 0, h, v, N, tol, maxiter, ux0, x_trim, ld_x, info, ld_info, status);
+    return e;
+  }
+#endif
   if (wants(sel, 1))
     e = launch_persistent(cfg, s ? trim_kernel<1, true> : trim_kernel<1, false>, F16_TRIM_THREADS, table_smem<1>(s), N,
                           F16_TRIM_THREADS, tabs, sel, h, v, N, tol, maxiter, g, x_trim, ld_x, info, ld_info, status);

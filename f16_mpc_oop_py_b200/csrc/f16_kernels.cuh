@@ -60,6 +60,9 @@ F16_DECLARE_LAUNCHERS
 cudaError_t launch_step_hifi_fast(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done);
+cudaError_t launch_trim_fast(const LaunchCfg&, const DevTables&, const BatchSel&, int FI, const double* h, const double* v,
+                             long long N, double tol, int maxiter, const double* ux0, double* x_trim, long long ld_x,
+                             double* info, long long ld_info, int* status);
 cudaError_t launch_step_lofi_fast(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done);

@@ -83,6 +83,124 @@ step_lofi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// trim_batch, F16_MATH_FAST: the same Nelder-Mead search (f16_model.cuh::nelder_mead_trim_with) with the objective on the
+// step kernel's arithmetic -- a third of the instructions per evaluation, and the search is ~2000 dependent evaluations
+// per thread.  obj_func clips thrust, the three surfaces and alpha into their ranges (env.py:240-250) and leaves the
+// flap state unclipped, so the precondition here is what calc_xdot_hifi / _lofi actually need (altitude inside the
+// density table, no NaN), not the step bounds; a trial point outside it takes the reference-order objective on the
+// standard image in global memory.
+// ------------------------------------------------------------------------------------------------------
+template <int FI>
+static __device__ __noinline__ double trim_cost_reference_order(const double* img_std, double h, double V, double lef_q, double u0,
+                                                                double u1, double u2, double u3, double u4, double xcg,
+                                                                unsigned* st) {
+  TrimPoint t;
+  t.h = h;
+  t.V = V;
+  t.lef_q = lef_q;
+  const double ux[5] = {u0, u1, u2, u3, u4};
+  unsigned s = 0;
+  const double c = trim_cost<FI>(img_std, t, ux, xcg, s);
+  *st = s;
+  return c;
+}
+
+template <int FI>
+struct TrimCostFast {
+  const double* img;      // the step image of this fidelity, in shared memory
+  const double* img_std;  // the standard image, in global memory (rare path)
+  __device__ __forceinline__ double operator()(const TrimPoint& t, const double (&ux)[5], double xcg, unsigned& st) const {
+    double x[18], u[4], xd[18];
+    trim_cost_inputs(t, ux, x, u);
+    // trim_state: phi = psi = beta = p = q = r = 0, theta = alpha; what can be out of range is the caller's h and V
+    const bool ok = (x[2] >= 0.0) & (x[2] <= 100000.0) & !either_nan(x[6], x[7]) & !either_nan(x[12], x[13]) &
+                    !either_nan(x[14], x[15]) & !either_nan(x[16], x[17]);
+    if (!ok) {
+      unsigned s = 0;
+      const double c = trim_cost_reference_order<FI>(img_std, t.h, t.V, t.lef_q, ux[0], ux[1], ux[2], ux[3], ux[4], xcg, &s);
+      st = s;
+      return c;
+    }
+    double uc[4];
+    fastmath::clip_commands(u, uc);
+    const bool inside = FI ? fastmath::calc_xdot_hifi<false>(img, x, uc, xcg, xd) : fastmath::calc_xdot_lofi<false>(img, x, uc, xcg, xd);
+    if (!inside) {
+      const double a = x[7] * (180.0 / 3.141592653589793), b = x[8] * (180.0 / 3.141592653589793);
+      st = FI ? hifi_envelope(a, b, x[13]) : lofi_envelope(a, b, x[13]);
+      return __builtin_huge_val();
+    }
+    st = 0;
+    return trim_cost_sum(xd);
+  }
+};
+
+struct TrimGuessFast {
+  double ux[5];
+};
+
+template <int FI>
+__global__ void __launch_bounds__(256, 1)
+trim_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ h_g, const double* __restrict__ v_g, long long N,
+                 double tol, int maxiter, TrimGuessFast guess, double* __restrict__ x_g, long long ld_x,
+                 double* __restrict__ info_g, long long ld_info, int* __restrict__ status) {
+  const double* img;
+  if (FI) {
+    stage_tables_tma<F16_FI_BYTES>(f16_smem, tabs.hifi_fast, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
+    img = reinterpret_cast<const double*>(f16_smem);
+#if defined(F16_FAST_LDS64)
+    img += tabs.zero;
+#endif
+  } else {
+    double* li = reinterpret_cast<double*>(f16_smem);
+    for (int i = threadIdx.x; i < F16_LOFI_STEP_IMG_DOUBLES; i += blockDim.x)
+      li[i] = i < F16_IMG_LOFI_DOUBLES ? tabs.lofi[i] : tabs.hifi_fast[F16_FI_POW + (i - F16_IMG_LOFI_DOUBLES)];
+    __syncthreads();
+    img = li;
+  }
+  const TrimCostFast<FI> cost{img, FI ? tabs.hifi : tabs.lofi};
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int own = owns<FI>(sel, n);
+    if (own == 0) continue;
+    double x[18];
+    TrimResult r;
+    if (own == 1) {
+      double ux[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) ux[k] = guess.ux[k];
+      const TrimPoint t = trim_point(h_g[n], v_g[n]);
+      r = nelder_mead_trim_with(cost, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux);
+      trim_state(t, ux, x);  // env.py:275-288: the optimiser's (unclipped) point
+    } else {
+      r.cost = qnan(); r.iterations = 0; r.fcalls = 0; r.converged = 0; r.status = ST_FIDELITY;
+#pragma unroll
+      for (int i = 0; i < 18; i++) x[i] = qnan();
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+    if (info_g) {
+      info_g[n] = r.cost;
+      info_g[ld_info + n] = (double)r.iterations;
+      info_g[2 * ld_info + n] = (double)r.fcalls;
+      info_g[3 * ld_info + n] = (double)r.converged;
+    }
+    if (status) status[n] = (int)r.status;
+  }
+}
+
+cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, int FI, const double* h,
+                             const double* v, long long N, double tol, int maxiter, const double* ux0, double* x_trim,
+                             long long ld_x, double* info, long long ld_info, int* status) {
+  if (N <= 0) return cudaSuccess;
+  TrimGuessFast g;
+  for (int k = 0; k < 5; k++) g.ux[k] = ux0[k];
+  if (FI)
+    return launch_persistent(cfg, trim_fast_kernel<1>, 256, FAST_SMEM_BYTES, N, 256, tabs, sel, h, v, N, tol, maxiter, g, x_trim,
+                             ld_x, info, ld_info, status);
+  return launch_persistent(cfg, trim_fast_kernel<0>, 256, F16_LOFI_STEP_IMG_DOUBLES * 8, N, 256, tabs, sel, h, v, N, tol, maxiter,
+                           g, x_trim, ld_x, info, ld_info, status);
+}
+
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*);
 
