@@ -799,3 +799,46 @@ def test_rollout_stats_equals_chunked_steps_and_summaries(f16, mode):
     assert rows[0][0] == n and rows[-1][1] == (b.status == 0).sum() and 0 < rows[-1][1] < n
     assert np.all(np.diff(rows[:, 1]) <= 0)           # survivors never come back
 
+@pytest.mark.gpu
+def test_step_beyond_2_to_31_elements(f16):
+    """maximum sizes: 2^27 + 5 aircraft -- plane offsets pass 2^31 elements (17 x 2^27 = 2.3e9), 19 GB of state built on the
+    device by tiling a 2^20-aircraft block; the tiles must come out of the step bit-identical to that block run alone"""
+    import ctypes
+    L = f16.lib
+    g = load_golden("xcg25")
+    nb = 1 << 20
+    reps = 128
+    n = nb * reps + 5
+    xb, ub = perturbed_trim(nb + 5, g["x_trim"], seed=99, frac=0.05)
+    small = f16.F16Batch(xb, ub, xcg=0.25)
+    small.step(K=7)
+    d_x, d_u, d_st = L.f16_dev_alloc(18 * n * 8), L.f16_dev_alloc(4 * n * 8), L.f16_dev_alloc(4 * n)
+    if not (d_x and d_u and d_st):
+        pytest.skip("not enough device memory for the 19 GB batch")
+    try:
+        for arr, d, planes in ((xb, d_x, 18), (ub, d_u, 4)):
+            for i in range(planes):
+                base = d + (i * n) * 8
+                assert L.f16_memcpy_h2d(base, arr[i, :nb].ctypes.data, nb * 8) == 0
+                filled = nb
+                while filled < nb * reps:                      # doubling device-to-device copies
+                    c = min(filled, nb * reps - filled)
+                    assert L.f16_memcpy_d2d(base + filled * 8, base, c * 8) == 0
+                    filled += c
+                tail = np.ascontiguousarray(arr[i, nb:nb + 5])
+                assert L.f16_memcpy_h2d(base + nb * reps * 8, tail.ctypes.data, 5 * 8) == 0
+        assert L.step_batch_dev(d_x, n, d_u, n, n, 7, 0.001, None, None, 1, None, 0.25, d_st, None) == 0
+        row = f16.state_summary_dev(d_x, n, n, d_st)
+        assert row[0] == n and row[1] == reps * int((small.status[:nb] == 0).sum()) + int((small.status[nb:] == 0).sum())
+        out = np.empty(nb)
+        for i in (0, 7, 17):                                    # first, a middle and the last plane (offset 17 n > 2^31)
+            for tile in (0, 77, reps - 1):
+                assert L.f16_memcpy_d2h(out.ctypes.data, d_x + (i * n + tile * nb) * 8, nb * 8) == 0
+                assert np.array_equal(out, small.x[i, :nb], equal_nan=True), (i, tile)
+            t5 = np.empty(5)
+            assert L.f16_memcpy_d2h(t5.ctypes.data, d_x + (i * n + reps * nb) * 8, 5 * 8) == 0
+            assert np.array_equal(t5, small.x[i, nb:], equal_nan=True)
+    finally:
+        for p in (d_x, d_u, d_st):
+            L.f16_dev_free(p)
+
