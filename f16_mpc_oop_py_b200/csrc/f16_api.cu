@@ -386,7 +386,7 @@ int linearise_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
   std::lock_guard<std::mutex> lk(G_mu);
   int rc = ensure();
   if (rc != F16_OK) return rc;
-  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || ld_x < N || ld_u < N || (scheme != 0 && scheme != 1) || !(eps > 0)) {
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || ld_x < N || ld_u < N || (scheme != 0 && scheme != 1) || !(eps >= 1e-12 && eps <= 1e3)) {
     set_err("linearise_batch_dev: bad argument");
     return F16_ERR_ARG;
   }
@@ -531,7 +531,7 @@ int linearise_batch(const double* x_soa, const double* u_soa, long long N, doubl
   std::lock_guard<std::mutex> lk(G_mu);
   int rc = ensure();
   if (rc != F16_OK) return rc;
-  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || (scheme != 0 && scheme != 1) || !(eps > 0)) {
+  if (N < 0 || (N > 0 && (!x_soa || !u_soa || !A || !B)) || (scheme != 0 && scheme != 1) || !(eps >= 1e-12 && eps <= 1e3)) {
     set_err("linearise_batch: bad argument");
     return F16_ERR_ARG;
   }

@@ -232,7 +232,9 @@ struct LinSmem {
 
 // The quotient of the finite difference, (f(x + eps e_c) - f(x)) / eps (env.py:330,339) or (f+ - f-) / (2 eps): the IEEE
 // quotient through div_by (f16_model.cuh) -- most entries of a Jacobian are exactly 0, which the compiler's division
-// sequence sends down its slow path.  Steps outside [1e-15, 1e15] use the plain division.
+// sequence sends down its slow path.  The entry points accept steps in [1e-12, 1e3] only; the kernel still carries the
+// plain division for a step outside [1e-15, 1e15] (never taken; with it ptxas lays the write-out loop out 8 % faster).
+static __device__ __noinline__ double div_plain(double a, double y) { return a / y; }
 struct FdQuot {
   double den, rden;
   bool inv_ok;

