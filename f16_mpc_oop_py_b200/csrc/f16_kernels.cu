@@ -244,6 +244,7 @@ struct FdQuot {
     inv_ok = den >= 1e-15 && den <= 1e15;
   }
   __device__ __forceinline__ double operator()(double num) const { return inv_ok ? div_by(num, den, rden) : div_plain(num, den); }
+  __device__ __forceinline__ double q(double num) const { return div_by(num, den, rden); }  // branch-free (write-out loop)
 };
 
 // evaluation order, dealt round-robin to the warps (a pass costs about the same whatever it recomputes: measured, a deal
@@ -407,7 +408,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         if (k < 324) {
           const int r = k / 18, col = k - r * 18;
           double v = t[k];
-          if (scheme == 0) v = (col == 17 && r < 12) ? zero_col : fd(v - f0[r]);  // env.py:330
+          if (scheme == 0) v = (col == 17 && r < 12) ? zero_col : fd.q(v - f0[r]);  // env.py:330
           if (col < 2) v = zero_col;
           if (void_all) v = qnan();
           Ao[k] = v;
@@ -418,7 +419,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         const int k = j * 32 + lane;
         if (k < 72) {
           double v = t[324 + k];
-          if (scheme == 0) v = k < 48 ? zero_col : fd(v - f0[k >> 2]);  // env.py:339; rows 0..11 of B are zero
+          if (scheme == 0) v = k < 48 ? zero_col : fd.q(v - f0[k >> 2]);  // env.py:339; rows 0..11 of B are zero
           if (void_all) v = qnan();
           Bo[k] = v;
         }
