@@ -87,6 +87,7 @@ def _load():
     L.f16_hifi_probe.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]
     L.f16_lofi_probe.argtypes = [c_vp] * 5 + [c_ll, c_vp]
     L.atmos_batch.argtypes = [c_vp, c_vp, c_ll, c_vp]
+    L.f16_div_probe.argtypes = [c_vp, c_vp, c_ll, c_vp]
     L.f16_dev_alloc.argtypes = [ctypes.c_ulonglong]
     L.f16_dev_alloc.restype = c_vp
     L.f16_dev_free.argtypes = [c_vp]

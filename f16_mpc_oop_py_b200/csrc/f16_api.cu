@@ -931,6 +931,23 @@ int f16_lofi_probe(const double* alpha_deg, const double* beta_deg, const double
   return F16_OK;
 }
 
+int f16_div_probe(const double* a, const double* b, long long N, double* out) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N <= 0 || !a || !b || !out) { set_err("f16_div_probe: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(2 * n * 8));
+  CK(G.b_out.reserve(3 * n * 8));
+  double* d = (double*)G.b_in.p;
+  H2D(d, a, n * 8);
+  H2D(d + n, b, n * 8);
+  CK(f16::strict::launch_div_probe(cfg(false), d, d + n, N, (double*)G.b_out.p));  // always the strict build's helpers
+  D2H(out, G.b_out.p, 3 * n * 8);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
 int atmos_batch(const double* alt, const double* vt, long long N, double* coeff_soa) {
   std::lock_guard<std::mutex> lk(G_mu);
   int rc = ensure();

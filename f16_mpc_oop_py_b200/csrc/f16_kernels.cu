@@ -740,6 +740,24 @@ cudaError_t launch_trim(const LaunchCfg& cfg, const DevTables& tabs, const Batch
   return e;
 }
 
+// parity probe of the two exact-division helpers: out[0][n] = F16_DIV(a, b), out[1][n] = div_by(a, b, RN(1 / b)), out[2][n] = a / b
+__global__ void __launch_bounds__(256)
+div_probe_kernel(const double* __restrict__ a, const double* __restrict__ b, long long N, double* __restrict__ out) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const double x = a[n], y = b[n];
+    out[n] = F16_DIV(x, y);
+    out[N + n] = div_by(x, y, 1.0 / y);
+    out[2 * N + n] = x / y;
+  }
+}
+
+cudaError_t launch_div_probe(const LaunchCfg& cfg, const double* a, const double* b, long long N, double* out) {
+  if (N <= 0) return cudaSuccess;
+  div_probe_kernel<<<grid_for(N, 256, cfg.sm_count * 8), 256, 0, cfg.stream>>>(a, b, N, out);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_hifi_probe(const LaunchCfg& cfg, const DevTables& tabs, const double* alpha, const double* beta,
                               const double* el, long long N, double* coef, int* cells, int* status) {
   if (N <= 0) return cudaSuccess;

@@ -47,6 +47,7 @@ struct LaunchCfg {
   cudaError_t launch_lofi_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta,         \
                                 const double* el, const double* dail, const double* drud, long long N, double* out); \
   cudaError_t launch_atmos(const LaunchCfg&, const double* alt, const double* vt, long long N, double* coeff);       \
+  cudaError_t launch_div_probe(const LaunchCfg&, const double* a, const double* b, long long N, double* out);        \
   cudaError_t launch_trim(const LaunchCfg&, const DevTables&, const BatchSel&, const double* h, const double* v,     \
                           long long N, double tol, int maxiter, const double* ux0, double* x_trim, long long ld_x,    \
                           double* info, long long ld_info, int* status);

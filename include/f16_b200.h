@@ -203,6 +203,9 @@ int f16_hifi_probe(const double *alpha_deg, const double *beta_deg, const double
 int f16_lofi_probe(const double *alpha_deg, const double *beta_deg, const double *el, const double *dail,
                    const double *drud, long long N, double *out);
 int atmos_batch(const double *alt, const double *vt, long long N, double *coeff_soa /* [3][N] */);
+/* the strict build's two division helpers against the device's IEEE division: out [3][N] = { branch-free division sequence,
+ * reciprocal + residual correction with RN(1/b), a / b } (csrc/f16_model.cuh: F16_DIV, div_by) */
+int f16_div_probe(const double *a, const double *b, long long N, double *out);
 
 /* ---- device memory / timing helpers so that callers need no CUDA binding of their own ---------------- */
 void *f16_dev_alloc(unsigned long long bytes);

@@ -842,3 +842,40 @@ def test_step_beyond_2_to_31_elements(f16):
         for p in (d_x, d_u, d_st):
             L.f16_dev_free(p)
 
+@pytest.mark.gpu
+def test_division_helpers_have_the_bits_of_the_device_division(f16):
+    """F16_DIV (the division sequence without its range test and slow-path branch) and div_by (rounded reciprocal + one
+    residual correction) against a / b ON THE DEVICE: ordinary operands over 60 decades, the model's own divisors (vt,
+    cos(theta), U^2 + W^2, ps), zero numerators, and numerators whose quotient sits on a rounding midpoint"""
+    import random
+    from fractions import Fraction  # noqa: F401
+    sys_path_tests = os.path.dirname(os.path.abspath(__file__))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ted", os.path.join(sys_path_tests, "test_exact_division.py"))
+    ted = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ted)
+    r = np.random.default_rng(17)
+    rnd = random.Random(17)
+    n = 2_000_000
+    a = r.uniform(-1, 1, n) * 10.0 ** r.integers(-30, 30, n)
+    b = r.uniform(0.5, 1, n) * 10.0 ** r.integers(-30, 30, n) * r.choice([-1.0, 1.0], n)
+    a[:1000] = 0.0
+    b[1000:200000] = r.uniform(0.01, 900, 199000)                    # vt
+    b[200000:400000] = np.cos(r.uniform(-1.57, 1.57, 200000))        # cos(theta)
+    b[400000:600000] = r.uniform(1e-4, 1e6, 200000)                  # U^2 + W^2
+    k = 600000
+    for y in (700.0, 0.9999, 11.32, 2116.2, 3.7e5) + tuple(r.uniform(0.01, 1e6, 40)):
+        hard = np.array(ted.hard_numerators(float(y), 2000, rnd))
+        a[k:k + hard.size] = hard
+        b[k:k + hard.size] = y
+        k += hard.size
+    out = np.empty((3, n))
+    assert f16.lib.f16_div_probe(a.ctypes.data, b.ctypes.data, n, out.ctypes.data) == 0
+    with np.errstate(all="ignore"):
+        host = a / b
+    assert np.array_equal(out[2].view(np.uint64), host.view(np.uint64))          # the device divides as IEEE 754 says
+    assert np.array_equal(out[0], out[2])                                        # values (a zero keeps its value, not its sign)
+    nz = a != 0
+    assert np.array_equal(out[0][nz].view(np.uint64), out[2][nz].view(np.uint64))
+    assert np.array_equal(out[1].view(np.uint64), out[2].view(np.uint64))
+
