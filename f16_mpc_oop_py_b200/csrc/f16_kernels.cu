@@ -408,7 +408,10 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         if (k < 324) {
           const int r = k / 18, col = k - r * 18;
           double v = t[k];
-          if (scheme == 0) v = (col == 17 && r < 12) ? zero_col : fd.q(v - f0[r]);  // env.py:330
+          if (scheme == 0) {  // env.py:330; the quotient is formed for every element and selected afterwards: a branch
+            const double qv = fd.q(v - f0[r]);  // around it would stop the 11 independent chains from interleaving
+            v = (col == 17 && r < 12) ? zero_col : qv;
+          }
           if (col < 2) v = zero_col;
           if (void_all) v = qnan();
           Ao[k] = v;
@@ -419,7 +422,10 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
         const int k = j * 32 + lane;
         if (k < 72) {
           double v = t[324 + k];
-          if (scheme == 0) v = k < 48 ? zero_col : fd.q(v - f0[k >> 2]);  // env.py:339; rows 0..11 of B are zero
+          if (scheme == 0) {  // env.py:339; rows 0..11 of B are zero
+            const double qv = fd.q(v - f0[k >> 2]);
+            v = k < 48 ? zero_col : qv;
+          }
           if (void_all) v = qnan();
           Bo[k] = v;
         }
