@@ -289,7 +289,7 @@ linearise_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
       const int k = warp == 0 ? 0 : warp - 3;
       const double ang = k == 0 ? xu0[7] : k == 1 ? xu0[8] : k == 2 ? xu0[4] : k == 3 ? xu0[3] : xu0[5];
       double sn, cs;
-#if defined(__CUDA_ARCH__) && !F16_FASTPATH
+#if defined(__CUDA_ARCH__)
       // the five angles decide together, exactly as trig_eval does, so that every variant of the kernel sees the same bits
       const bool nb = trig_small(xu0[7]) & trig_small(xu0[8]) & trig_small(xu0[4]) & trig_small(xu0[3]) & trig_small(xu0[5]);
       if (nb) sincos_nb(ang, sn, cs);
