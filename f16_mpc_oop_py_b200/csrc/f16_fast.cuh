@@ -255,13 +255,17 @@ static inline void make_dense_law(const LqrLaw& l, LqrDense& d) {
   }
 }
 
+// COLMASK != 0: the set of gain columns is known at compile time (the reference's own law: its nine MPC states,
+// parameters.py:135) -- no branch per column, so the column updates interleave; 0: read it from the law.
+#define F16_LQR_MPC_COLMASK 0x30F98  // states 3, 4, 7, 8, 9, 10, 11, 16, 17
+template <int COLMASK = 0>
 F16_FD void lqr_action_dense(const LqrDense& l, const double (&x)[18], const double (&u_in)[4], double (&u)[4]) {
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < 18; i++) {
-    if ((l.colmask >> i) & 1) {
+    if (COLMASK ? ((COLMASK >> i) & 1) : ((l.colmask >> i) & 1)) {
       const double e = x[i] - l.xr[i];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -681,7 +685,7 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
 
 // K fused Euler steps of env.py::step from step k; stops (k < K on return) at the first state that fails step_ok or
 // leaves the tables.  The state is not advanced on the failing step.
-template <bool LQR, bool LIBM_TRIG, int FI = 1>
+template <bool LQR, bool LIBM_TRIG, int FI = 1, int COLMASK = 0>
 F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg, double dt,
                      int k, int K) {
   double uc[4];
@@ -694,7 +698,7 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
     double xd[18];
     if (LQR) {
       double u[4];
-      lqr_action_dense(*lqr, x, u_in, u);
+      lqr_action_dense<COLMASK>(*lqr, x, u_in, u);
       clip_commands(u, uc);
     }
     if (!(FI ? calc_xdot_hifi<LIBM_TRIG>(img, x, uc, xcg, xd) : calc_xdot_lofi<LIBM_TRIG>(img, x, uc, xcg, xd))) break;
@@ -715,17 +719,17 @@ F16_FD unsigned exact_status(const double (&x)[18], const double (&u_in)[4]) {
 }
 
 // the whole step_batch semantics for one aircraft: returns the status word, k = steps taken
-template <bool LQR, int FI = 1>
+template <bool LQR, int FI = 1, int COLMASK = 0>
 F16_FD unsigned step_aircraft(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg,
                               double dt, int K, int& k) {
   k = 0;
   if (either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3])) return K > 0 ? step_bounds(x, u_in) : 0u;
-  k = run_steps<LQR, false, FI>(img, x, u_in, lqr, xcg, dt, 0, K);
+  k = run_steps<LQR, false, FI, COLMASK>(img, x, u_in, lqr, xcg, dt, 0, K);
   if (k == K) return 0u;
   unsigned st = exact_status<FI>(x, u_in);  // stopped early: the exact status word of the frozen state
   if (st) return st;
   // none of the reference's stop conditions: an Euler angle beyond 2^30 rad -- carry on with libm's trig
-  k = run_steps<LQR, true, FI>(img, x, u_in, lqr, xcg, dt, k, K);
+  k = run_steps<LQR, true, FI, COLMASK>(img, x, u_in, lqr, xcg, dt, k, K);
   return k == K ? 0u : exact_status<FI>(x, u_in);
 }
 

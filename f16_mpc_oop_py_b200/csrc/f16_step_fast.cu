@@ -17,7 +17,7 @@ __constant__ fastmath::LqrDense c_lqr_fast;
 // ------------------------------------------------------------------------------------------------------
 constexpr int FAST_SMEM_BYTES = F16_FI_BYTES + 16;
 
-template <bool SMEM, bool LQR, int THREADS>
+template <bool SMEM, bool LQR, int THREADS, int COLMASK = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
                       const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
@@ -45,7 +45,7 @@ step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
     for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
     const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
     int k;
-    const unsigned st = fastmath::step_aircraft<LQR>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
+    const unsigned st = fastmath::step_aircraft<LQR, 1, COLMASK>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
 #pragma unroll
     for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
     if (status) status[n] = (int)st;
@@ -229,6 +229,11 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   }
   int threads = cfg.step_threads;
   StepKern k = lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads);
+  if (lqr_host && cfg.smem_tables && threads == 384) {  // the reference's own column set at the default CTA size: compile-time columns
+    fastmath::LqrDense d;
+    fastmath::make_dense_law(*lqr_host, d);
+    if (d.colmask == F16_LQR_MPC_COLMASK) k = step_hifi_fast_kernel<true, true, 384, F16_LQR_MPC_COLMASK>;
+  }
   const int smem = cfg.smem_tables ? FAST_SMEM_BYTES : 0;
   return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
 }
