@@ -495,6 +495,9 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
 // half_rho().  Look-ups as lofi_F16_AeroData.c:12-368 (5-degree alpha grid with linear extrapolation, |beta| grid 0:5:30,
 // elevator grid -24:12:24), totals as nlplant.c:258-286,333-377 with every leading-edge-flap term zero (:256,295-319).
 // alpha is not confined to the hifi tables here, so it takes the reduced sincos like the Euler angles.
+// The prologue (trig, atmosphere, reciprocals, kinematics) and the epilogue (accelerations, moments, actuators) repeat
+// calc_xdot_hifi's on purpose: the hifi function is the headline kernel's loop body, and its schedule (168 registers, no
+// spills, 59 % of the FP64 peak) does not survive being cut into shared pieces -- ptxas is that sensitive here.
 // ------------------------------------------------------------------------------------------------------
 #define F16_LOFI_STEP_IMG_DOUBLES (F16_IMG_LOFI_DOUBLES + 2 * F16_FI_NPOW)
 
