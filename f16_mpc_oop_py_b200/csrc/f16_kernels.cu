@@ -90,11 +90,13 @@ nlplant_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ xu_g, lo
   double* buf = reinterpret_cast<double*>(f16_smem + PipeSmem<FI, SMEM, 17>::OFF) + warp * (17 * 32);
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, n, n < N);
+  // an aircraft of the other fidelity is neither copied nor evaluated here (mixed batches: the other launch takes it)
+  pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, n, n < N && owns<FI>(sel, n) != 0);
   for (; n < N; n += stride) {
     double xu[17], xd[18];
     pipe_take<17>(buf, lane, xu);
-    pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, n + stride, n + stride < N);
+    const long long nn = n + stride;
+    pipe_issue<17, 0>(buf, lane, xu_g, ld_in, nullptr, 0, nn, nn < N && owns<FI>(sel, nn) != 0);
     const int own = owns<FI>(sel, n);
     if (own == 0) continue;
     unsigned st = ST_FIDELITY;
@@ -122,11 +124,12 @@ calc_xdot_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
   double* buf = reinterpret_cast<double*>(f16_smem + PipeSmem<FI, SMEM, 22>::OFF) + warp * (22 * 32);
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, n, n < N);
+  pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, n, n < N && owns<FI>(sel, n) != 0);
   for (; n < N; n += stride) {
     double xin[22], x[18], u[4], xd[18];
     pipe_take<22>(buf, lane, xin);
-    pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, n + stride, n + stride < N);
+    const long long nn = n + stride;
+    pipe_issue<18, 4>(buf, lane, x_g, ld_x, u_g, ld_u, nn, nn < N && owns<FI>(sel, nn) != 0);
 #pragma unroll
     for (int i = 0; i < 18; i++) x[i] = xin[i];
 #pragma unroll
