@@ -57,7 +57,7 @@ step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
 // step_batch, lofi, F16_MATH_FAST: the Stevens-Lewis model on the same arithmetic (fastmath::calc_xdot_lofi).  Its step
 // image is 7 KB (lofi tables + the centre table of half_rho), copied into shared memory by the CTA itself.
 // ------------------------------------------------------------------------------------------------------
-template <bool LQR, int THREADS>
+template <bool LQR, int THREADS, int COLMASK = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 step_lofi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
                       const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
@@ -75,7 +75,7 @@ step_lofi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, lo
     for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
     const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
     int k;
-    const unsigned st = fastmath::step_aircraft<LQR, 0>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
+    const unsigned st = fastmath::step_aircraft<LQR, 0, COLMASK>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
 #pragma unroll
     for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
     if (status) status[n] = (int)st;
@@ -253,6 +253,11 @@ cudaError_t launch_step_lofi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   }
   const int smem = F16_LOFI_STEP_IMG_DOUBLES * 8;
   StepKern k = lqr_host ? step_lofi_fast_kernel<true, 384> : step_lofi_fast_kernel<false, 384>;
+  if (lqr_host) {  // the reference's own column set: compile-time columns (as in the hifi kernel)
+    fastmath::LqrDense d;
+    fastmath::make_dense_law(*lqr_host, d);
+    if (d.colmask == F16_LQR_MPC_COLMASK) k = step_lofi_fast_kernel<true, 384, F16_LQR_MPC_COLMASK>;
+  }
   return launch_persistent(cfg, k, 384, smem, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
 }
 
