@@ -250,10 +250,10 @@ struct FdQuot {
   __device__ __forceinline__ double q(double num) const { return div_by(num, den, rden); }  // branch-free (write-out loop)
 };
 
-// evaluation order, dealt round-robin to the warps (a pass costs about the same whatever it recomputes: measured, a deal
-// balanced by estimated cost was slower); the base point last
+// evaluation order, dealt round-robin to the warps (warp w takes entries w and w + 8): the three columns that recompute the
+// table look-ups are paired with plain columns, the sin/cos columns with each other; the base point last
 
-__constant__ signed char c_lin_order[16] = {7, 8, 13, 2, 6, 14, 15, 3, 4, 5, 9, 10, 11, 12, 16, 22};
+__constant__ signed char c_lin_order[16] = {7, 8, 13, 2, 6, 14, 15, 3, 9, 10, 11, 12, 16, 4, 5, 22};
 
 template <int FI>
 __global__ void __launch_bounds__(F16_LIN_WARPS * 32, 1)
