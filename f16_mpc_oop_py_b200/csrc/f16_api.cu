@@ -60,7 +60,7 @@ struct State {
   // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
-  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk;
 };
 
 State G;
@@ -215,7 +215,7 @@ void f16_shutdown(void) {
   cudaSetDevice(G.device);
   cudaStreamSynchronize(G.stream);
   for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush, &G.b_l1, &G.b_l2,
-                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum})
+                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum, &G.b_perm, &G.b_pscr, &G.b_px, &G.b_pu, &G.b_pxcg, &G.b_pst, &G.b_pk})
     b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
@@ -364,6 +364,60 @@ int calc_xdot_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
   return F16_OK;
 }
 
+// A mixed batch (per-aircraft fidelity flags) for the fused step: ordered by fidelity first, so that each of the two launches
+// runs on a contiguous range with every lane busy (f16_partition.cu).  Applies when the reorder is amortised
+// (N >= 4096 aircraft, K >= 8 steps); *handled = false leaves the call to the per-lane masking of the kernels.
+static int step_partitioned(double* d_x, long long ld_x, const double* d_u, long long ld_u, long long N, int K, double dt,
+                            const f16_lqr_t* lqr, const unsigned char* d_fi, const double* d_xcg, double xcg_default,
+                            int* d_status, int* d_steps, bool* handled) {
+  *handled = false;
+  if (!d_fi || N < 4096 || K < 8 || N >= (1LL << 31)) return F16_OK;
+  const size_t n = (size_t)N;
+  const int n_cta = f16::partition::n_cta(N);
+  // scratch is optional: when the device cannot hold a second copy of the batch the masked path does the job
+  if (G.b_perm.reserve(n * 4) != cudaSuccess || G.b_pscr.reserve((size_t)n_cta * 6 * 4 + 64) != cudaSuccess ||
+      G.b_px.reserve(18 * n * 8) != cudaSuccess || G.b_pu.reserve(4 * n * 8) != cudaSuccess ||
+      G.b_pst.reserve(n * 4) != cudaSuccess || G.b_pk.reserve(n * 4) != cudaSuccess ||
+      (d_xcg && G.b_pxcg.reserve(n * 8) != cudaSuccess)) {
+    cudaGetLastError();
+    return F16_OK;
+  }
+  const f16::LaunchCfg c = cfg(G.smem_tables);
+  unsigned* perm = (unsigned*)G.b_perm.p;
+  unsigned* scr = (unsigned*)G.b_pscr.p;
+  long long* totals_dev = (long long*)(scr + (size_t)n_cta * 6 + 2);  // 8-byte aligned: n_cta * 24 + 8 bytes in
+  CK(f16::partition::launch_build(c, d_fi, N, perm, totals_dev, scr));
+  long long tot[3];
+  CK(cudaMemcpyAsync(tot, totals_dev, sizeof(tot), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
+  const long long n1 = tot[0], n0 = tot[1], nbad = tot[2];
+  double* px = (double*)G.b_px.p;
+  double* pu = (double*)G.b_pu.p;
+  double* pxcg = d_xcg ? (double*)G.b_pxcg.p : nullptr;
+  int* pst = (int*)G.b_pst.p;
+  int* pk = (int*)G.b_pk.p;
+  CK(f16::partition::launch_gather_f64(c, d_x, ld_x, px, N, 18, perm, N));
+  CK(f16::partition::launch_gather_f64(c, d_u, ld_u, pu, N, 4, perm, N));
+  if (d_xcg) CK(f16::partition::launch_gather_f64(c, d_xcg, N, pxcg, N, 1, perm, N));
+  const f16::LqrLaw* law = reinterpret_cast<const f16::LqrLaw*>(lqr);
+  if (n1 > 0)
+    CK(DISPATCH(launch_step, c, tabs(), sel_of(nullptr, 1, pxcg, xcg_default), px, N, pu, N, n1, K, dt, law, pst, pk));
+  if (n0 > 0)
+    CK(DISPATCH(launch_step, c, tabs(), sel_of(nullptr, 0, pxcg ? pxcg + n1 : nullptr, xcg_default), px + n1, N, pu + n1, N, n0, K,
+                dt, law, pst + n1, pk + n1));
+  if (nbad > 0) {  // neither model: the state stays as it is, status = F16_ST_FIDELITY, no step taken
+    std::vector<int> bad((size_t)nbad, (int)F16_ST_FIDELITY);
+    CK(cudaMemcpyAsync(pst + n1 + n0, bad.data(), (size_t)nbad * 4, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemsetAsync(pk + n1 + n0, 0, (size_t)nbad * 4, G.stream));
+    CK(cudaStreamSynchronize(G.stream));  // `bad` is pageable and goes out of scope
+  }
+  CK(f16::partition::launch_scatter_f64(c, px, N, d_x, ld_x, 18, perm, N));
+  if (d_status) CK(f16::partition::launch_scatter_i32(c, pst, d_status, perm, N));
+  if (d_steps) CK(f16::partition::launch_scatter_i32(c, pk, d_steps, perm, N));
+  *handled = true;
+  return F16_OK;
+}
+
 int step_batch_dev(double* x_soa, long long ld_x, const double* u_soa, long long ld_u, long long N, int K, double dt,
                    const f16_lqr_t* lqr, const unsigned char* fi, int fi_default, const double* xcg, double xcg_default,
                    int* status, int* steps_done) {
@@ -374,6 +428,10 @@ int step_batch_dev(double* x_soa, long long ld_x, const double* u_soa, long long
   if (lqr && (lqr->n_sel < 0 || lqr->n_sel > 18)) { set_err("step_batch_dev: lqr.n_sel out of range"); return F16_ERR_ARG; }
   if (lqr) for (int j = 0; j < lqr->n_sel; j++) if (lqr->sel[j] < 0 || lqr->sel[j] > 17) { set_err("step_batch_dev: lqr.sel out of range"); return F16_ERR_ARG; }
   // tables go to shared memory whenever the launch does real work; a handful of aircraft-steps read them via L2
+  bool handled = false;
+  if ((rc = step_partitioned(x_soa, ld_x, u_soa, ld_u, N, K, dt, lqr, fi, xcg, xcg_default, status, steps_done, &handled)) != F16_OK)
+    return rc;
+  if (handled) return F16_OK;
   const bool smem = G.smem_tables && (N * (long long)(K > 0 ? K : 1) >= 4096);
   CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, N, K, dt,
               reinterpret_cast<const f16::LqrLaw*>(lqr), status, steps_done));
@@ -468,10 +526,16 @@ int step_batch(double* x_soa, const double* u_soa, long long N, int K, double dt
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, x_soa, 18 * n * 8);
   H2D(G.b_in2.p, u_soa, 4 * n * 8);
-  const bool smem = G.smem_tables && (N * (long long)(K > 0 ? K : 1) >= 4096);
-  CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (double*)G.b_in.p, N,
-              (const double*)G.b_in2.p, N, N, K, dt, reinterpret_cast<const f16::LqrLaw*>(lqr), (int*)G.b_st.p,
-              (int*)G.b_st2.p));
+  bool handled = false;
+  if ((rc = step_partitioned((double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, K, dt, lqr, d_fi, d_xcg, xcg_default,
+                             (int*)G.b_st.p, (int*)G.b_st2.p, &handled)) != F16_OK)
+    return rc;
+  if (!handled) {
+    const bool smem = G.smem_tables && (N * (long long)(K > 0 ? K : 1) >= 4096);
+    CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), (double*)G.b_in.p, N,
+                (const double*)G.b_in2.p, N, N, K, dt, reinterpret_cast<const f16::LqrLaw*>(lqr), (int*)G.b_st.p,
+                (int*)G.b_st2.p));
+  }
   D2H(x_soa, G.b_in.p, 18 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);
   if (steps_done) D2H(steps_done, G.b_st2.p, n * 4);

@@ -85,6 +85,18 @@ cudaError_t launch_summary(const LaunchCfg&, const double* x, long long ld, long
 int summary_grid(const LaunchCfg&, long long N);
 }  // namespace stats
 
+// f16_partition.cu: a mixed batch ordered by fidelity for the fused step (stable three-way partition, gather, scatter)
+namespace partition {
+cudaError_t launch_build(const LaunchCfg&, const unsigned char* fi, long long N, unsigned* perm, long long* totals_dev,
+                         unsigned* scratch);
+cudaError_t launch_gather_f64(const LaunchCfg&, const double* src, long long ld_src, double* dst, long long ld_dst, int planes,
+                              const unsigned* perm, long long N);
+cudaError_t launch_scatter_f64(const LaunchCfg&, const double* src, long long ld_src, double* dst, long long ld_dst, int planes,
+                               const unsigned* perm, long long N);
+cudaError_t launch_scatter_i32(const LaunchCfg&, const int* src, int* dst, const unsigned* perm, long long N);
+int n_cta(long long N);
+}  // namespace partition
+
 // FP64 FMA micro-benchmark (f16_peak.cu): returns flops executed
 cudaError_t launch_dfma_peak(cudaStream_t stream, int sm_count, long long iters, double* sink, double* flops);
 

@@ -446,6 +446,36 @@ def test_step_mixed_fidelity_batch_equals_separate_batches(f16, mode):
         assert np.array_equal(mixed.x[:, m], part.x, equal_nan=True) and np.array_equal(mixed.status[m], part.status)
 
 
+@pytest.mark.parametrize("with_law", [False, True])
+def test_step_large_mixed_batch_is_partitioned_by_fidelity(f16, mode, with_law):
+    """a mixed batch big enough for the fidelity partition (f16_partition.cu: stable three-way partition, gather, two
+    launches on contiguous ranges, scatter): same bits as the two fidelities run apart, whatever the interleaving;
+    aircraft with an invalid flag keep their state and report F16_ST_FIDELITY"""
+    g = load_golden("xcg25")
+    n = 20000 + 37
+    x, u = perturbed_trim(n, g["x_trim"], seed=78, frac=0.04)
+    r = np.random.default_rng(5)
+    fi = (r.uniform(size=n) < 0.6).astype(np.uint8)
+    fi[[3, 4097, n - 1]] = 7                                    # neither model
+    xcg = np.where(r.uniform(size=n) < 0.5, 0.25, 0.35)
+    law = None
+    if with_law:
+        sel = list(g["mpc_x_idx"])
+        K = np.zeros((3, 9))
+        K[0, [2, 5]] = [-3.0, -0.8]
+        law = f16.make_lqr(K, sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+    mixed = f16.F16Batch(x, u, fi_flag=fi, xcg=xcg)
+    mixed.step(K=60, lqr=law)
+    for f in (0, 1):
+        m = fi == f
+        part = f16.F16Batch(x[:, m], u[:, m], fi_flag=f, xcg=xcg[m])
+        part.step(K=60, lqr=law)
+        assert np.array_equal(mixed.x[:, m], part.x, equal_nan=True) and np.array_equal(mixed.status[m], part.status)
+        assert np.array_equal(mixed.steps_done[m], part.steps_done)
+    bad = fi == 7
+    assert np.all(mixed.status[bad] == 1 << 22) and np.all(mixed.steps_done[bad] == 0) and np.array_equal(mixed.x[:, bad], x[:, bad])
+
+
 # ---------------------------------------------------------------------------------------------------------
 # linearise_batch (env.py:294-342; BASELINE cfg 4)
 # ---------------------------------------------------------------------------------------------------------
