@@ -164,7 +164,9 @@ int state_summary_batch(const double *x_soa /* [18][N] */, long long N, const in
 int step_batch_stats(double *x_soa, const double *u_soa, long long N, int K, int snap_every, double dt, const f16_lqr_t *lqr,
                      const unsigned char *fi, int fi_default, const double *xcg, double xcg_default, double *rows, int *status);
 
-/* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) --------- */
+/* ---- batched entry points, DEVICE buffers (asynchronous on f16_stream(); ld = plane stride) ---------
+ * step_batch_dev with a per-aircraft fi array (N >= 4096, K >= 8) orders the batch by fidelity on the device first
+ * (csrc/f16_partition.cu) and synchronises the stream once to read the class sizes. */
 int Nlplant_batch_dev(const double *xu_soa, long long ld_in, double *xdot_soa, long long ld_out, const unsigned char *fi,
                       int fi_default, const double *xcg, double xcg_default, long long N, int *status);
 int calc_xdot_batch_dev(const double *x_soa, long long ld_x, const double *u_soa, long long ld_u, double *xdot_soa,
