@@ -65,8 +65,8 @@ partial_kernel(const double* __restrict__ x, long long ld, long long N, const in
       const double v = x[i * ld + n];
       if (PASS == 1) {
         s[i] += v;
-        mn[i] = fmin(mn[i], v);
-        mx[i] = fmax(mx[i], v);
+        mn[i] = v < mn[i] ? v : mn[i];  // a NaN never wins a comparison: skipped, as fmin / fmax would
+        mx[i] = v > mx[i] ? v : mx[i];
       } else {
         const double d = v - mean[i];
         s[i] = fma(d, d, s[i]);
