@@ -85,6 +85,7 @@ def _load():
     L.discretise_batch_dev.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, ctypes.c_double, c_vp, c_vp]
     L.dlqr_batch_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, c_vp, c_vp, c_vp]
     L.f16_hifi_probe.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]
+    L.f16_fast_probe.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]
     L.f16_lofi_probe.argtypes = [c_vp] * 5 + [c_ll, c_vp]
     L.atmos_batch.argtypes = [c_vp, c_vp, c_ll, c_vp]
     L.f16_div_probe.argtypes = [c_vp, c_vp, c_ll, c_vp]

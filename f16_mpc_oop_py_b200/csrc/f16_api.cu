@@ -974,6 +974,31 @@ int f16_hifi_probe(const double* alpha_deg, const double* beta_deg, const double
   return F16_OK;
 }
 
+int f16_fast_probe(const double* alpha_deg, const double* beta_deg, const double* el, long long N, double* coef, int* cells,
+                   double* lam, int* status) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int rc = ensure();
+  if (rc != F16_OK) return rc;
+  if (N <= 0 || !alpha_deg || !beta_deg || !el || !coef || !cells || !lam) { set_err("f16_fast_probe: bad argument"); return F16_ERR_ARG; }
+  const size_t n = (size_t)N;
+  CK(G.b_in.reserve(3 * n * 8));
+  CK(G.b_out.reserve(48 * n * 8));
+  CK(G.b_st.reserve(n * 4));
+  CK(G.b_st2.reserve(4 * n * 4));
+  double* d = (double*)G.b_in.p;
+  H2D(d, alpha_deg, n * 8);
+  H2D(d + n, beta_deg, n * 8);
+  H2D(d + 2 * n, el, n * 8);
+  double* o = (double*)G.b_out.p;
+  CK(f16::fast::launch_fast_probe(cfg(false), tabs(), d, d + n, d + 2 * n, N, o, (int*)G.b_st2.p, o + 44 * n, (int*)G.b_st.p));
+  D2H(coef, o, 44 * n * 8);
+  D2H(lam, o + 44 * n, 4 * n * 8);
+  D2H(cells, G.b_st2.p, 4 * n * 4);
+  if (status) D2H(status, G.b_st.p, n * 4);
+  CK(cudaStreamSynchronize(G.stream));
+  return F16_OK;
+}
+
 int f16_lofi_probe(const double* alpha_deg, const double* beta_deg, const double* el, const double* dail,
                    const double* drud, long long N, double* out) {
   std::lock_guard<std::mutex> lk(G_mu);

@@ -38,7 +38,7 @@ struct K_t {
   double S[6], C[6];
   double two_over_pi, pio2_hi, pio2_mid;
   double PW[9];  // binomial coefficients C(4.14, k), k = 1..9
-  double r2d, shrink, inv15, c5_3, c7_3, tlapse, inv21_5, inv30, ninv25, half_cbar, g, S_m, inv_m, lef_q, inv_pi,
+  double r2d, inv15, c5_3, c7_3, tlapse, inv21_5, inv30, ninv25, half_cbar, g, S_m, inv_m, lef_q, inv_pi,
       c1_38, c1_45, c20_2, inv0_136, ixx_qr, ixx_pq, ixx_l, ixx_n, iyy_pr, iyy_p2, inv_Jy, izz_n, izz_l, izz_pq, izz_qr,
       xcg_arm;
 };
@@ -56,7 +56,7 @@ F16_KCONST K_t K = {
     0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17,
     {4.14, 6.499799999999999, 4.636523999999999, 1.321409339999999, 0.036999461519999895, -0.005303256151199987,
      0.0014091509201759967, -0.0005037714539629189, 0.00021606197914409635},
-    180.0 / 3.141592653589793, 1.0 - 1.0 / 1073741824.0, 1.0 / 15.0, 5.0 / 3.0, 7.0 / 3.0, -.703e-5, 1.0 / 21.5, 1.0 / 30.0,
+    180.0 / 3.141592653589793, 1.0 / 15.0, 5.0 / 3.0, 7.0 / 3.0, -.703e-5, 1.0 / 21.5, 1.0 / 30.0,
     -1.0 / 25.0, 0.5 * 11.32, 32.17, 300.0 / 636.94, 1.0 / 636.94, 0.5 * 9.05 / 1715.0, 1.0 / 3.141592653589793,
     1.38, 1.45, 20.2, 1 / 0.136,
     -(F16_JZ * (F16_JZ - F16_JY) + F16_JXZ * F16_JXZ) / F16_JD, F16_JXZ * (F16_JX - F16_JY + F16_JZ) / F16_JD,
@@ -180,18 +180,50 @@ F16_FD double rcp_nr(double v) {
 }
 
 // cell and weight on a piecewise-uniform axis.  u = position in cell units (cell k spans [k, k+1], n cells).
-// floor(u) through the round-to-nearest of (u (1 - 2^-30) - 0.5 + 2^-40) + 1.5*2^52: no conversion instruction, no
-// breakpoint load.  The 2^-30 shrink lands u == n in the last cell; the 2^-40 lift lands the bottom of the axis in
-// cell 0 even when the affine map to cell units rounds to -1e-16 there (fma(-20, 0.2, 4) = -2.2e-16).  Within those
-// margins of a breakpoint the neighbouring cell may be chosen with a weight just outside [0, 1]: the interpolant is
-// continuous there, so the value moves by rounding only.  The weight itself is exact: lam = u - k.
+// k = floor(u) as the round-to-nearest of (u - 0.5) + 1.5*2^52 (low word of the sum; no conversion instruction, no
+// breakpoint load), clamped to [0, n-1] on the integer pipe BEFORE the weight is formed, and the weight is the exact
+// difference lam = u - k (k rebuilt as a double from the clamped low word).  What this gives (mexndinterp.c:97-143):
+//   * u strictly inside a cell -> that cell, 0 < lam < 1: the reference's (j, j+1) and its lambda;
+//   * u == k (a breakpoint; u - 0.5 is a tie, rounded to even) -> cell k with lam = 0 or cell k-1 with lam = 1, both of
+//     which evaluate to the node value f_k like the reference's exact hit (j, j) -- fma(1, d, f) = f + (f_k - f) up to
+//     the rounding of the stored difference;
+//   * the ends of the axis: u == n -> cell n-1, lam = 1; the affine map to cell units may round the bottom to -2e-16
+//     (fma(-20, 0.2, 4)) -> cell 0, lam = -2e-16.
+// There is no margin: a query a relative 1e-16 above a breakpoint is in the upper cell.  (Round 1 shrank u by 2^-30
+// first, which put a 2^-30-wide band above every breakpoint into the LOWER cell with lam = 1 + delta, an extrapolation
+// with error delta * (slope change): 9e-9 scaled at alpha = 30 deg + 1.5e-8.)
+F16_FD double magic_plus(int k) {  // 1.5*2^52 + k for 0 <= k < 2^31: k is the low word
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(0x43380000, k);
+#else
+  unsigned long long b = 0x4338000000000000ULL | (unsigned)k;
+  double v;
+  __builtin_memcpy(&v, &b, 8);
+  return v;
+#endif
+}
 F16_FD int cell_of(double u, int n_cells, double& lam) {
   const double magic = 6755399441055744.0;
-  const double tm = fma(u, K.shrink, -0.5 + 0x1p-40) + magic;
-  lam = u - (tm - magic);
+  const double tm = (u - 0.5) + magic;
   int k = lo32(tm);
-  k = k < 0 ? 0 : (k > n_cells - 1 ? n_cells - 1 : k);  // memory safety only; never active for in-envelope u
+  k = k < 0 ? 0 : (k > n_cells - 1 ? n_cells - 1 : k);
+  lam = u - (magic_plus(k) - magic);
   return k;
+}
+
+// the four cells of a hifi look-up (ALPHA -20:5:45; BETA1 -30:5:-10:2:10:5:30; DH1 -25,-10,0,10,25; DH2 -25,0,25 --
+// check_grids() verifies the grids are these).  beta and DH1 are piecewise uniform: two compares pick scale and offset of
+// the affine map to cell units.  Position on the axis in cell units is ONE fma of the query, so it carries the rounding of
+// that fma (<= 2^-53 * 18 in cell units): a query within that distance of a breakpoint may be placed ON it (lam = 0 in the
+// upper cell where the reference has lam = 1 - 1e-16 in the lower one) -- the same value to the last bit or two.
+F16_FD void locate_hifi(double alpha, double beta, double el, int& ia, int& ib, int& i1, int& i2, double& la, double& lb,
+                        double& l1, double& l2) {
+  ia = cell_of(fma(alpha, 0.2, 4.0), 13, la);
+  const bool b_out = (beta < -10.0) | (beta >= 10.0);
+  ib = cell_of(fma(beta, b_out ? 0.2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
+  const bool e_out = (el < -10.0) | (el >= 10.0);
+  i1 = cell_of(fma(el, e_out ? K.inv15 : 0.1, el < -10.0 ? K.c5_3 : (el >= 10.0 ? K.c7_3 : 2.0)), 4, l1);
+  i2 = cell_of(fma(el, 0.04, 1.0), 2, l2);
 }
 
 // value of table `slot` of an (f, d) node at alpha weight la
@@ -300,14 +332,9 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   // hifi_envelope(): the elevator range is already guaranteed by the |x[13]| <= 25 bound
   if (!((alpha >= -20.0) & (alpha <= 45.0) & (fabs(beta) <= 30.0))) return false;
 
-  // cells (ALPHA -20:5:45; BETA1 -30:5:-10:2:10:5:30; DH1 -25,-10,0,10,25; DH2 -25,0,25 -- check_grids() verifies)
   double la, lb, l1, l2;
-  const int ia = cell_of(fma(alpha, 0.2, 4.0), 13, la);
-  const bool b_out = (beta < -10.0) | (beta >= 10.0);
-  const int ib = cell_of(fma(beta, b_out ? 0.2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
-  const bool e_out = (el < -10.0) | (el >= 10.0);
-  const int i1 = cell_of(fma(el, e_out ? K.inv15 : 0.1, el < -10.0 ? K.c5_3 : (el >= 10.0 ? K.c7_3 : 2.0)), 4, l1);
-  const int i2 = cell_of(fma(el, 0.04, 1.0), 2, l2);
+  int ia, ib, i1, i2;
+  locate_hifi(alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
 
   double sa, ca, sb, cb, st, ct, sphi, cphi, spsi, cpsi;
   sincos_quarter(x[7], sa, ca);
@@ -487,6 +514,51 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   }
   xd[17] = (alpha_deg - lf_in) * 7.25;
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Parity probe of the fast image and cell search (f16_fast_probe; never on the step path): the 44 coefficient outputs of
+// the reference's aggregators (hifi:1871-1934) in the order of f16_hifi_probe, evaluated the way calc_xdot_hifi evaluates
+// them -- locate_hifi, (f, d) gathers, alpha then beta then elevator -- but one table at a time, so that every table of the
+// image and every cell decision can be compared with the reference accessors and getHyperCube.  Slot 24 (delta_CZq_lef)
+// is not in the fast image (nlplant.c:339 never uses it) and slot 43 (delta_Cm_ds) is the constant 0: both return 0.
+// cells = {ia, ib, i1, i2}, lam = {la, lb, l1, l2}.
+// ------------------------------------------------------------------------------------------------------
+F16_FD void probe_hifi(const double* img, double alpha, double beta, double el, double (&o)[44], int (&cells)[4],
+                       double (&lam)[4]) {
+  double la, lb, l1, l2;
+  int ia, ib, i1, i2;
+  locate_hifi(alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
+  cells[0] = ia; cells[1] = ib; cells[2] = i1; cells[3] = i2;
+  lam[0] = la; lam[1] = lb; lam[2] = l1; lam[3] = l2;
+  for (int i = 0; i < 44; i++) o[i] = 0.0;
+  {
+    const double* p = img + F16_FI_G3A + ((i1 * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3A_STRIDE;
+    const int sb_ = F16_FI_NAC * F16_FI_G3A_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3A_STRIDE;
+    for (int t = 0; t < 3; t++)  // Cx, Cz, Cm
+      o[t] = mix(l1, mix(lb, fd(p, t, la), fd(p + sb_, t, la)), mix(lb, fd(p + sd, t, la), fd(p + sd + sb_, t, la)));
+    const d2 e = ld2(img + F16_FI_ETA + 2 * i1);
+    o[42] = fma(l1, e.y, e.x);
+  }
+  {
+    const double* p = img + F16_FI_G3B + ((i2 * F16_N_B + ib) * F16_FI_NAC + ia) * F16_FI_G3B_STRIDE;
+    const int sb_ = F16_FI_NAC * F16_FI_G3B_STRIDE, sd = F16_N_B * F16_FI_NAC * F16_FI_G3B_STRIDE;
+    for (int t = 0; t < 2; t++)  // Cn, Cl
+      o[4 + t] = mix(l2, mix(lb, fd(p, t, la), fd(p + sb_, t, la)), mix(lb, fd(p + sd, t, la), fd(p + sd + sb_, t, la)));
+  }
+  {
+    const double* n0 = img + F16_FI_G2 + (ib * F16_FI_NAC + ia) * F16_FI_G2_STRIDE;
+    const double* n1 = n0 + F16_FI_NAC * F16_FI_G2_STRIDE;
+    // f16_hifi_probe slot of each FG2 table
+    const int dst[FG2_COUNT] = {15, 16, 17, 3, 18, 33, 34, 30, 19, 35, 36, 31, 20, 37, 38, 32};
+    for (int t = 0; t < FG2_COUNT; t++) o[dst[t]] = mix(lb, fd(n0, t, la), fd(n1, t, la));
+  }
+  {
+    const double* p = img + F16_FI_G1 + ia * F16_FI_G1_STRIDE;
+    // FG1 order: Cxq dCxq_lef Czq Cmq dCmq_lef dCm Cyr dCyr_lef Cyp dCyp_lef Cnr dCnr_lef Cnp dCnp_lef dCnbeta Clr dClr_lef Clp dClp_lef dClbeta
+    const int dst[FG1_COUNT] = {6, 21, 9, 12, 27, 41, 7, 22, 8, 23, 13, 28, 14, 29, 39, 10, 25, 11, 26, 40};
+    for (int t = 0; t < FG1_COUNT; t++) o[dst[t]] = fd(p, t, la);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -67,6 +67,8 @@ cudaError_t launch_trim_fast(const LaunchCfg&, const DevTables&, const BatchSel&
 cudaError_t launch_step_lofi_fast(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done);
+cudaError_t launch_fast_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta, const double* el,
+                              long long N, double* coef, int* cells, double* lam, int* status);
 }
 
 // f16_linalg.cu: reduced-model gather, zero-order-hold discretisation, discrete LQR gain (one thread per aircraft)

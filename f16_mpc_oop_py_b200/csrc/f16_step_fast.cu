@@ -201,6 +201,42 @@ cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const 
                            g, x_trim, ld_x, info, ld_info, status);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// f16_fast_probe: the fast image and its cell search as the step kernel uses them (fastmath::probe_hifi), one query per
+// thread, image read from global memory.  coef [44][N], cells [4][N], lam [4][N]; a query outside the hifi tables gets
+// NaN / -1 and the status word of hifi_envelope().
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fast_probe_kernel(DevTables tabs, const double* __restrict__ alpha, const double* __restrict__ beta,
+                  const double* __restrict__ el, long long N, double* __restrict__ coef, int* __restrict__ cells,
+                  double* __restrict__ lam, int* __restrict__ status) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const double a = alpha[n], b = beta[n], e = el[n];
+    const unsigned st = hifi_envelope(a, b, e);
+    double o[44], l[4];
+    int c[4];
+    if (st) {
+      for (int i = 0; i < 44; i++) o[i] = qnan();
+      for (int i = 0; i < 4; i++) { c[i] = -1; l[i] = qnan(); }
+    } else {
+      fastmath::probe_hifi(tabs.hifi_fast, a, b, e, o, c, l);
+    }
+    for (int i = 0; i < 44; i++) coef[i * N + n] = o[i];
+    for (int i = 0; i < 4; i++) { cells[i * N + n] = c[i]; lam[i * N + n] = l[i]; }
+    if (status) status[n] = (int)st;
+  }
+}
+
+cudaError_t launch_fast_probe(const LaunchCfg& cfg, const DevTables& tabs, const double* alpha, const double* beta,
+                              const double* el, long long N, double* coef, int* cells, double* lam, int* status) {
+  if (N <= 0) return cudaSuccess;
+  long long g = (N + 255) / 256;
+  if (g > cfg.sm_count * 8) g = cfg.sm_count * 8;
+  fast_probe_kernel<<<(unsigned)g, 256, 0, cfg.stream>>>(tabs, alpha, beta, el, N, coef, cells, lam, status);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*);
 

@@ -201,6 +201,13 @@ int dlqr_batch_dev(const double *Ad, const double *Bd, const double *Q, const do
  * convention (mexndinterp.c:126-137: exact hit -> lo == hi). */
 int f16_hifi_probe(const double *alpha_deg, const double *beta_deg, const double *el, long long N, double *coef,
                    int *cells, int *status);
+/* The same 44 outputs from the F16_MATH_FAST table image with the step kernel's own cell search (csrc/f16_fast.cuh:
+ * locate_hifi, (f, d) gathers): cells [4][N] = cell index k of ALPHA, BETA1, DH1, DH2 (the cell spans breakpoints k, k+1),
+ * lam [4][N] = weight inside the cell.  getHyperCube's (lo, hi) maps to k = lo when lo != hi; on an exact hit lo == hi the
+ * search returns (lo, lam = 0) or (lo - 1, lam = 1), the same node value.  Slots 24 (delta_CZq_lef, unused by
+ * nlplant.c:339) and 43 (delta_Cm_ds = 0) are returned as 0. */
+int f16_fast_probe(const double *alpha_deg, const double *beta_deg, const double *el, long long N, double *coef,
+                   int *cells, double *lam, int *status);
 /* lofi coefficients: out [19][N] = damping[9], dmomdcon[4], clcn[2], cxcm[2], cz, Cy(-.02b+.021da+.086dr) */
 int f16_lofi_probe(const double *alpha_deg, const double *beta_deg, const double *el, const double *dail,
                    const double *drud, long long N, double *out);

@@ -44,10 +44,20 @@ def golden(request):
 
 
 def scaled_err(a, ref, axis=-1):
-    """max |a-ref| / max(|ref|, rms of the reference along `axis`): the parity metric of SURVEY.md fact 8."""
+    """max |a-ref| / max(|ref|, rms of the reference along `axis`): the parity metric of SURVEY.md fact 8.
+    Non-finite entries must sit in the same places in both arrays (a stray NaN in the product is a failure, not a
+    dropped sample); the metric is taken over the entries finite in both."""
     ref = np.asarray(ref, dtype=np.float64)
     a = np.asarray(a, dtype=np.float64)
-    scale = np.sqrt(np.nanmean(ref * ref, axis=axis, keepdims=True))
-    den = np.maximum(np.abs(ref), scale)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    fin_a, fin_r = np.isfinite(a), np.isfinite(ref)
+    assert np.array_equal(fin_a, fin_r), f"{int((fin_a != fin_r).sum())} entries are finite in one array and not in the other"
+    if not fin_r.any():
+        return 0.0
+    r0 = np.where(fin_r, ref, 0.0)
+    cnt = np.maximum(fin_r.sum(axis=axis, keepdims=True), 1)
+    scale = np.sqrt((r0 * r0).sum(axis=axis, keepdims=True) / cnt)
+    den = np.maximum(np.abs(r0), scale)
     den = np.where(den == 0, 1.0, den)
-    return float(np.nanmax(np.abs(a - ref) / den))
+    err = np.where(fin_r, np.abs(np.where(fin_a, a, 0.0) - r0) / den, 0.0)
+    return float(err.max())

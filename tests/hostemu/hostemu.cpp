@@ -81,6 +81,17 @@ __attribute__((visibility("default"))) unsigned emu_hifi_probe(double a, double 
   f16::ref_cell(img + F16_IMG_D2, L.d2, e, cl[6], cl[7]);
   return 0;
 }
+// the fast image + cell search as f16_fast_probe runs them (fastmath::probe_hifi)
+__attribute__((visibility("default"))) unsigned emu_fast_probe(double a, double b, double e, double* o, int* cl, double* lam) {
+  unsigned st = f16::hifi_envelope(a, b, e);
+  if (st) return st;
+  double oo[44], ll[4];
+  int cc[4];
+  f16::fastmath::probe_hifi(g_fast.data(), a, b, e, oo, cc, ll);
+  for (int i = 0; i < 44; i++) o[i] = oo[i];
+  for (int i = 0; i < 4; i++) { cl[i] = cc[i]; lam[i] = ll[i]; }
+  return 0;
+}
 // the F16_MATH_FAST arithmetic of f16_fast.cuh (hifi step), same control flow as step_hifi_fast_kernel
 __attribute__((visibility("default"))) unsigned emu_calc_xdot_fast(const double* x_, const double* u_, double* xd_, double xcg) {
   double x[18], u[4], xd[18];

@@ -115,8 +115,15 @@ def _probe_points():
     return np.array(pts).T.copy()
 
 
-def test_hifi_lookup_bit_exact(f16, oracle):
-    f16.lib.f16_set_math_mode(f16.MATH_STRICT)
+@pytest.fixture
+def strict_mode(f16):
+    """strict math for the duration of one test; the previous mode is restored (VERDICT r01 weak #10)"""
+    prev = f16.lib.f16_set_math_mode(f16.MATH_STRICT)
+    yield
+    f16.lib.f16_set_math_mode(prev)
+
+
+def test_hifi_lookup_bit_exact(f16, oracle, strict_mode):
     a, b, e = _probe_points()
     n = a.size
     coef = np.empty((44, n))
@@ -152,8 +159,7 @@ def test_hifi_lookup_outside_grid_is_flagged(f16):
     assert np.isnan(coef).all()
 
 
-def test_lofi_lookup(f16, oracle):
-    f16.lib.f16_set_math_mode(f16.MATH_STRICT)
+def test_lofi_lookup(f16, oracle, strict_mode):
     r = np.random.default_rng(4)
     n = 20000
     a = np.concatenate([r.uniform(-20, 90, n - 60), np.arange(-20, 100, 5.0)[:24], np.arange(-20, 100, 5.0)[:24] + 1e-13,
@@ -182,6 +188,29 @@ def test_lofi_lookup(f16, oracle):
         assert np.array_equal(out[row], ref[row]), row
     assert np.max(np.abs(out[17] - ref[17])) < 1e-15
     assert np.allclose(out[18], ref[18], rtol=0, atol=1e-17)
+
+
+def test_fast_image_and_cell_search_on_the_device(f16, oracle):
+    """f16_fast_probe: the F16_MATH_FAST table image with the step kernel's own cell search (csrc/f16_fast.cuh:
+    locate_hifi) against getHyperCube (mexndinterp.c:97-143) and the reference aggregators (hifi:1871-1934): random points,
+    every breakpoint of ALPHA / BETA1 / DH1 / DH2, +-1 ulp, and the 1e-12 .. 1e-6 bands on both sides (VERDICT r01 #1)."""
+    from _probe import check_fast_probe, probe_points
+    pts = probe_points()
+    n = pts.shape[1]
+    a, b, e = (np.ascontiguousarray(pts[i]) for i in range(3))
+    coef, cells, lam = np.empty((44, n)), np.empty((4, n), dtype=np.int32), np.empty((4, n))
+    st = np.zeros(n, dtype=np.int32)
+    assert f16.lib.f16_fast_probe(a.ctypes.data, b.ctypes.data, e.ctypes.data, n, coef.ctypes.data, cells.ctypes.data,
+                                  lam.ctypes.data, st.ctypes.data) == 0
+    assert not st.any()
+    s = check_fast_probe(oracle, pts, coef, cells, lam)
+    assert s["worst_coef_err"] < 1e-13, s
+    # outside the tables: flagged, NaN, cell -1
+    a2, b2, e2 = np.array([45.0001, 0.0, 0.0]), np.array([0.0, -30.5, 0.0]), np.array([0.0, 0.0, 25.5])
+    c2, k2, l2, s2 = np.empty((44, 3)), np.empty((4, 3), dtype=np.int32), np.empty((4, 3)), np.zeros(3, dtype=np.int32)
+    assert f16.lib.f16_fast_probe(a2.ctypes.data, b2.ctypes.data, e2.ctypes.data, 3, c2.ctypes.data, k2.ctypes.data,
+                                  l2.ctypes.data, s2.ctypes.data) == 0
+    assert list(s2) == [1 << 18, 1 << 19, 1 << 20] and np.isnan(c2).all() and (k2 == -1).all()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -309,9 +338,10 @@ def test_step_batch_perturbed_trim(f16, oracle, mode, tag):
     fb.step(K=2000)
     alive = (rst == 0) & (fb.status == 0)
     assert alive.mean() > 0.5
-    # an aircraft may leave the envelope one step earlier or later when it grazes a bound: compare survivors,
-    # and require the two implementations to agree on who survived except for such grazing cases
-    assert np.mean(rst != fb.status) < 0.01
+    # An aircraft that crosses a bound within rounding of step 2000 may be stopped by one implementation and not (yet) by
+    # the other: at most one such grazing case in 512 is accepted (none has been observed); everything else must carry the
+    # oracle's status word.
+    assert int((rst != fb.status).sum()) <= 1, np.flatnonzero(rst != fb.status)
     assert scaled_err(fb.x[:, alive], ref[:, alive]) < TOL_TRAJ
     frozen = (rst != 0) & (fb.status == rst)
     if frozen.any():
@@ -635,6 +665,68 @@ def test_trim_then_linearise_full_cfg4_grid(f16):
     assert np.allclose(A[:, 13, 13], -20.2) and np.allclose(A[:, 14, 14], -20.2) and np.allclose(A[:, 15, 15], -20.2)
 
 
+def test_cfg4_full_grid_jacobians_against_the_oracle(f16, oracle):
+    """BASELINE cfg 4 at its stated size as a PARITY test: all 64 x 64 device-computed trim points,
+    forward (env.py:294-342, eps 1e-5) and central A/B from linearise_batch against the same scheme looped over the
+    reference .so at every point, <= 1e-8 absolute."""
+    hh, vv = np.meshgrid(np.linspace(5000, 40000, 64), np.linspace(300, 900, 64), indexing="ij")
+    x, opt = f16.trim(hh.ravel(), vv.ravel(), fi=1, xcg=0.35)
+    ok = opt["success"] & (opt["status"] == 0)
+    assert ok.sum() >= 4000, int(ok.sum())
+    xs, us = np.ascontiguousarray(x[:, ok]), np.ascontiguousarray(x[12:16, ok])
+    fb = f16.F16Batch(xs, us, xcg=0.35)
+    for scheme, code in (("forward", 0), ("central", 1)):
+        A, B, _, _ = fb.linearise(xs, us, scheme=scheme)
+        rA, rB, rst = oracle.linearise_batch(xs.copy(), us.copy(), 1e-5, code, 1, 0.35, checker(oracle))
+        assert np.array_equal(fb.last_status, rst) and not rst.any()
+        eA, eB = np.abs(A - rA), np.abs(B - rB)
+        assert eA.max() < TOL_JAC and eB.max() < TOL_JAC, (scheme, eA.max(), eB.max(), np.unravel_index(np.argmax(eA), eA.shape))
+
+
+_BENCH_SAMPLE_CACHE = {}
+
+
+def _bench_batch_sample(oracle, workload, n, K, n_sample=256):
+    """bench.py's own batch for `workload` (same generator, same seed as rank 0) and the oracle's final state of a strided
+    sample of it after K Euler steps (cached across the math-mode parametrisation: ~6 s of CPU per workload)."""
+    import bench
+    from f16_mpc_oop_py_b200.shard import rank_seed
+    tag, xcg = ("xcg35", 0.35) if workload == "lqr" else ("xcg25", 0.25)
+    x_trim, u_trim, mpc_idx = bench.trim_state(tag)
+    x, u = bench.perturbed_trim(n, x_trim, u_trim, seed=rank_seed(0xF16, 0))
+    idx = np.arange(0, n, n // n_sample)
+    key = (workload, n, K)
+    if key not in _BENCH_SAMPLE_CACHE:
+        law = None
+        if workload == "lqr":
+            law = orc_make_lqr(-load_golden(tag)["K_lqr"], mpc_idx, x_trim[mpc_idx], u_trim, rows=[1, 2, 3])
+        _BENCH_SAMPLE_CACHE[key] = oracle.step_batch(np.ascontiguousarray(x[:, idx]), np.ascontiguousarray(u[:, idx]), K, 0.001,
+                                                     1, xcg, law, checker(oracle))
+    return x, u, idx, xcg, x_trim, u_trim, mpc_idx, _BENCH_SAMPLE_CACHE[key]
+
+
+@pytest.mark.parametrize("workload", ["open", "lqr"])
+def test_bench_workload_final_state_sample_against_the_oracle(f16, oracle, mode, workload):
+    """the bench's OWN run -- cfg 2 (2^20 aircraft x 10 000 fused Euler steps, open loop, xcg 0.25) and
+    cfg 5's closed loop (u = u0 - K (x - x_trim) with the reference's K_lqr, xcg 0.35, 2^20 of its 8 Mi aircraft per GPU) --
+    sampled at 256 aircraft against the reference .so after the full 10 s: <= 1e-9 scaled, status words equal."""
+    n, K = 1 << 20, 10000
+    x, u, idx, xcg, x_trim, u_trim, mpc_idx, (ref, rst) = _bench_batch_sample(oracle, workload, n, K)
+    law = None
+    if workload == "lqr":
+        law = f16.make_lqr(-load_golden("xcg35")["K_lqr"], mpc_idx, x_trim[mpc_idx], u_trim, rows=[1, 2, 3])
+    fb = f16.F16Batch(x, u, xcg=xcg)
+    fb.step(K=K, lqr=law)
+    st = fb.status[idx]
+    # who stopped: the oracle's status word, except an aircraft that crosses a bound within rounding of the last step
+    assert int((st != rst).sum()) <= 1, np.flatnonzero(st != rst)
+    alive = (st == 0) & (rst == 0)
+    assert alive.mean() > (0.95 if workload == "lqr" else 0.9), alive.mean()
+    err = scaled_err(fb.x[:, idx][:, alive], ref[:, alive])
+    assert err < TOL_TRAJ, err
+    assert np.array_equal(fb.steps_done[idx][alive], np.full(int(alive.sum()), K))
+
+
 def test_trim_edges(f16):
     x, opt = f16.trim(np.zeros(0), np.zeros(0))
     assert x.shape == (18, 0)
@@ -768,6 +860,65 @@ def test_step_on_the_envelope_corners(f16, oracle, mode):
     assert ok.sum() > 200
     assert np.all(np.abs(fb.x[:, ok] - ref[:, ok]) <= 1e-13 * np.maximum(np.abs(ref[:, ok]), 1.0))
     assert np.array_equal(fb.x[:, ~ok], x[:, ~ok])      # stopped aircraft keep their state
+
+def _dt1_derivative_error(f16, oracle, x, u, xcg, fi=1):
+    """One Euler step with dt = 1.0 through step_batch, so that x1 - x0 IS the derivative the step kernel computed (a
+    derivative error is not scaled down by dt = 1e-3): |x1 - fl(x0 + xdot_ref)| in units of max(|xdot_ref|, rms of that
+    derivative over the batch), after allowing the one rounding of the sum (1 ulp of x1)."""
+    ref, rst = oracle.calc_xdot_batch(x, u, fi, xcg, checker(oracle))
+    fb = f16.F16Batch(x, u, fi_flag=fi, xcg=xcg, dt=1.0)
+    fb.step(K=1)
+    assert np.array_equal(fb.status, np.zeros_like(fb.status)) and not rst.any()
+    assert (fb.steps_done == 1).all() and np.isfinite(fb.x).all()
+    want = x + ref
+    scale = np.maximum(np.abs(ref), np.sqrt(np.mean(ref * ref, axis=1, keepdims=True)))
+    scale = np.where(scale == 0, 1.0, scale)
+    excess = np.maximum(np.abs(fb.x - want) - np.spacing(np.abs(want)), 0.0)
+    return excess / scale
+
+
+@pytest.mark.parametrize("xcg", [0.25, 0.35])
+def test_step_kernel_derivative_in_the_breakpoint_bands(f16, oracle, mode, xcg):
+    """VERDICT r01 #1/#2: the derivative of the STEP kernels (in fast mode: f16_fast.cuh on the device, with the device's own
+    rcp / sincos code) at alpha, beta, elevator on every interior breakpoint, +-1 ulp and +-{1e-12 .. 1e-6} of a cell width,
+    <= 1e-12 scaled against the reference .so.  dt = 1 makes x1 - x0 the derivative."""
+    from _inputs import breakpoint_band_states
+    x = breakpoint_band_states(X_TRIM_XCG25)
+    u = np.ascontiguousarray(np.tile(X_TRIM_XCG25[12:16][:, None], (1, x.shape[1])))
+    err = _dt1_derivative_error(f16, oracle, x, u, xcg)
+    w = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < TOL_DERIV, (err.max(), w, x[[7, 8, 13], w[1]] * [180 / np.pi, 180 / np.pi, 1])
+
+
+@pytest.mark.parametrize("fi", [1, 0])
+def test_step_kernel_derivative_over_the_envelope(f16, oracle, mode, fi):
+    """the same dt = 1 derivative check of the step kernels on 20 000 random in-envelope states and on perturbed-trim
+    states (VERDICT r01 weak #2: the device-side 1e-12 check of the arithmetic that carries the headline number)"""
+    n = 20000
+    xu = random_envelope_xu(n, seed=23, hifi=bool(fi))
+    r = np.random.default_rng(6)
+    x = np.vstack([xu, r.uniform(-30, 30, (1, n))])
+    x[2] = r.uniform(0, 60000, n)
+    u = np.stack([r.uniform(500, 20000, n), r.uniform(-30, 30, n), r.uniform(-25, 25, n), r.uniform(-35, 35, n)])
+    err = _dt1_derivative_error(f16, oracle, np.ascontiguousarray(x), np.ascontiguousarray(u), 0.25, fi)
+    assert err.max() < TOL_DERIV, (err.max(), np.unravel_index(np.argmax(err), err.shape))
+    xp, up = perturbed_trim(n, X_TRIM_XCG25, seed=12)
+    err = _dt1_derivative_error(f16, oracle, xp, up, 0.35, fi)
+    assert err.max() < TOL_DERIV, (err.max(), np.unravel_index(np.argmax(err), err.shape))
+
+
+@pytest.mark.parametrize("xcg", [0.25, 0.35])
+def test_calc_xdot_in_the_breakpoint_bands(f16, oracle, mode, xcg):
+    """calc_xdot_batch (the one-shot kernels) on the same band states, both builds"""
+    from _inputs import breakpoint_band_states
+    x = breakpoint_band_states(X_TRIM_XCG25)
+    u = np.ascontiguousarray(np.tile(X_TRIM_XCG25[12:16][:, None], (1, x.shape[1])))
+    ref, rst = oracle.calc_xdot_batch(x, u, 1, xcg, checker(oracle))
+    fb = f16.F16Batch(x, u, xcg=xcg)
+    out = fb._calc_xdot(x, u)
+    assert not rst.any() and not fb.last_status.any()
+    assert scaled_err(out, ref) < TOL_DERIV
+
 
 # ---------------------------------------------------------------------------------------------------------
 # end-of-run statistics reduced on the device (f16_stats.cu; SURVEY 8e / 8f rank 4)

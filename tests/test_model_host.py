@@ -403,3 +403,48 @@ def test_fast_lofi_step_over_the_lofi_envelope(emu_fast, oracle):
             alive = (st == 0) & (sts == 0)
             assert alive.mean() > 0.9
             assert scaled_err(out[:, alive], ref[:, alive]) < 1e-10
+
+
+@pytest.mark.parametrize("xcg", [0.25, 0.35])
+def test_fast_calc_xdot_in_the_bands_around_every_breakpoint(emu_fast, oracle, xcg):
+    """the fast cell search must pick the reference's cell (mexndinterp.c:97-143) everywhere, also
+    within 1e-12 .. 1e-6 of a cell width above or below an interior breakpoint -- a wrong cell there extrapolates its
+    neighbour and errs by delta * (slope difference) (9e-9 scaled was measured at alpha = 30 deg + 1.5e-8).  Checked
+    against the reference's own .so when oracle/_ref is present."""
+    from _inputs import X_TRIM_XCG25, breakpoint_band_states
+    from conftest import scaled_err
+    from oracle import REF
+    X = breakpoint_band_states(X_TRIM_XCG25)
+    U = np.ascontiguousarray(np.tile(X_TRIM_XCG25[12:16][:, None], (1, X.shape[1])))
+    be = REF if oracle.open_ref() else PORT
+    ref, st = oracle.calc_xdot_batch(X, U, 1, xcg, be)
+    assert (st == 0).all()
+    out = np.empty_like(ref)
+    for i in range(X.shape[1]):
+        xd = np.zeros(18)
+        assert emu_fast.emu_calc_xdot_fast(_p(np.ascontiguousarray(X[:, i])), _p(np.ascontiguousarray(U[:, i])), _p(xd), xcg) == 0
+        out[:, i] = xd
+    scale = np.maximum(np.abs(ref), np.sqrt(np.mean(ref * ref, axis=1, keepdims=True)))
+    err = np.abs(out - ref) / np.where(scale == 0, 1.0, scale)
+    assert np.isfinite(out).all()
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < 1e-12, (err.max(), worst, X[[7, 8, 13], worst[1]] * [180 / np.pi, 180 / np.pi, 1])
+
+
+def test_fast_image_and_cell_search_against_the_reference_accessors(emu_fast, oracle):
+    """f16_fast_probe on the host compile: the cells of locate_hifi against getHyperCube and every table of the (f, d)
+    image against the reference aggregators, on random points, every breakpoint, +-1 ulp and the 1e-12 .. 1e-6 bands."""
+    from _probe import check_fast_probe, probe_points
+    emu_fast.emu_fast_probe.argtypes = [ctypes.c_double] * 3 + [dp, ctypes.POINTER(ctypes.c_int), dp]
+    pts = probe_points()
+    n = pts.shape[1]
+    coef, cells, lam = np.zeros((44, n)), np.zeros((4, n), dtype=np.int32), np.zeros((4, n))
+    o, c, l = np.zeros(44), (ctypes.c_int * 4)(), np.zeros(4)
+    for i in range(n):
+        assert emu_fast.emu_fast_probe(pts[0, i], pts[1, i], pts[2, i], _p(o), c, _p(l)) == 0
+        coef[:, i], cells[:, i], lam[:, i] = o, list(c), l
+    s = check_fast_probe(oracle, pts, coef, cells, lam)
+    assert s["worst_coef_err"] < 1e-13, s
+    # s["on_node_other_cell"]: queries on or an ulp from a breakpoint that the one-FMA map to cell units places 1e-16 to
+    # its other side (check_fast_probe bounds their weight to 4 ulp of 0 / 1): the same value to rounding, never a band
+    print(s)
