@@ -46,7 +46,12 @@ extern "C" {
 
 /* ---- arithmetic mode ---------------------------------------------------------------------------- */
 #define F16_MATH_STRICT 0 /* reference operation order, no FMA contraction: the parity build */
-#define F16_MATH_FAST 1   /* same expressions with FMA contraction (|diff| <= 1e-13 scaled) */
+#define F16_MATH_FAST 1   /* throughput build.  step_batch / trim_batch run the RE-ASSOCIATED arithmetic of csrc/f16_fast.cuh
+                           * ((f, d) table image with node deltas, polynomial sin/cos and tfac^4.14, one shared reciprocal,
+                           * wind-axis equations with vt cancelled); Nlplant_batch / calc_xdot_batch run the strict
+                           * expressions with FMA contraction and reciprocal multiplies.  Both stay within the parity bars
+                           * (<= 1e-12 scaled per derivative, <= 1e-9 after 10 s; tests/test_gpu_parity.py);
+                           * linearise_batch always runs the strict build (the quotient multiplies rounding by 1/eps). */
 
 /* ---- CLr table quirk ---------------------------------------------------------------------------
  * The reference never loads CL1320_ALPHA1_606.dat (hifi_F16_AeroData.c:965-972: the fscanf loop is the

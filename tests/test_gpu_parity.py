@@ -675,12 +675,22 @@ def test_cfg4_full_grid_jacobians_against_the_oracle(f16, oracle):
     assert ok.sum() >= 4000, int(ok.sum())
     xs, us = np.ascontiguousarray(x[:, ok]), np.ascontiguousarray(x[12:16, ok])
     fb = f16.F16Batch(xs, us, xcg=0.35)
+    # Bar: 1e-8 absolute plus the quotient's own noise floor, 4 ulp(|f_i|) / h (h = eps forward, 2 eps central).  The
+    # reference's OWN source compiled with -O3 -march=native moves the forward A by 2.3e-8 on the 900 ft/s navigation rows
+    # (profiles/r02_jacobian_noise_floor.md): one ulp of f divided by eps is already 1.1e-8 there.  Everywhere |f_i| < 100
+    # the bar is the plain 1e-8.
+    xd = fb._calc_xdot(xs, us)
     for scheme, code in (("forward", 0), ("central", 1)):
         A, B, _, _ = fb.linearise(xs, us, scheme=scheme)
         rA, rB, rst = oracle.linearise_batch(xs.copy(), us.copy(), 1e-5, code, 1, 0.35, checker(oracle))
         assert np.array_equal(fb.last_status, rst) and not rst.any()
+        h = 1e-5 * (2 if code else 1)
+        bar = TOL_JAC + 4 * np.spacing(np.abs(xd)).T[:, :, None] / h          # [N][18][1]
         eA, eB = np.abs(A - rA), np.abs(B - rB)
-        assert eA.max() < TOL_JAC and eB.max() < TOL_JAC, (scheme, eA.max(), eB.max(), np.unravel_index(np.argmax(eA), eA.shape))
+        assert (eA <= bar).all() and (eB <= bar).all(), (scheme, eA.max(), eB.max(), np.unravel_index(np.argmax(eA - bar), eA.shape))
+        over = eA > TOL_JAC                                                    # only navigation rows may use the allowance
+        assert not over[:, 2:, :].any() and eB.max() < TOL_JAC, (scheme, np.argwhere(over[:, 2:, :])[:4])
+        print(f"cfg4 {scheme}: max |dA| {eA.max():.2e} (rows 0-1: {int(over.sum())} of {over[:, :2].size} entries above 1e-8), max |dB| {eB.max():.2e}")
 
 
 _BENCH_SAMPLE_CACHE = {}
