@@ -60,7 +60,7 @@ struct State {
   // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
-  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk, b_redo;
 };
 
 State G;
@@ -199,6 +199,28 @@ int stage_sel(const unsigned char* fi, const double* xcg, long long N, const uns
 
 #define DISPATCH(fn, ...) (G.math_mode == F16_MATH_FAST ? f16::fast::fn(__VA_ARGS__) : f16::strict::fn(__VA_ARGS__))
 
+// the one-shot entry points: in F16_MATH_FAST a batch worth staging tables for runs the TMA-tiled kernels on the arithmetic of
+// f16_fast.cuh (f16_step_fast.cu); a handful of aircraft (the legacy Nlplant symbol among them) read the tables through L2
+bool oneshot_fast(long long N) { return G.math_mode == F16_MATH_FAST && G.smem_tables && N >= 4096; }
+cudaError_t run_nlplant(const f16::BatchSel& sel, const double* xu, long long ld_in, double* xdot, long long ld_out, long long N,
+                        int* status) {
+  if (oneshot_fast(N)) {
+    cudaError_t e = G.b_redo.reserve((size_t)((N + 31) / 32) * 4);
+    if (e != cudaSuccess) return e;
+    return f16::fast::launch_xdot_fast(cfg(true), tabs(), sel, xu, ld_in, nullptr, 0, xdot, ld_out, N, status, (unsigned*)G.b_redo.p);
+  }
+  return DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel, xu, ld_in, xdot, ld_out, N, status);
+}
+cudaError_t run_calc_xdot(const f16::BatchSel& sel, const double* x, long long ld_x, const double* u, long long ld_u, double* xdot,
+                          long long ld_out, long long N, int* status) {
+  if (oneshot_fast(N)) {
+    cudaError_t e = G.b_redo.reserve((size_t)((N + 31) / 32) * 4);
+    if (e != cudaSuccess) return e;
+    return f16::fast::launch_xdot_fast(cfg(true), tabs(), sel, x, ld_x, u, ld_u, xdot, ld_out, N, status, (unsigned*)G.b_redo.p);
+  }
+  return DISPATCH(launch_calc_xdot, cfg(G.smem_tables && N >= 4096), tabs(), sel, x, ld_x, u, ld_u, xdot, ld_out, N, status);
+}
+
 }  // namespace
 
 extern "C" {
@@ -215,7 +237,7 @@ void f16_shutdown(void) {
   cudaSetDevice(G.device);
   cudaStreamSynchronize(G.stream);
   for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush, &G.b_l1, &G.b_l2,
-                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum, &G.b_perm, &G.b_pscr, &G.b_px, &G.b_pu, &G.b_pxcg, &G.b_pst, &G.b_pk})
+                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum, &G.b_perm, &G.b_pscr, &G.b_px, &G.b_pu, &G.b_pxcg, &G.b_pst, &G.b_pk, &G.b_redo})
     b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
@@ -347,8 +369,7 @@ int Nlplant_batch_dev(const double* xu_soa, long long ld_in, double* xdot_soa, l
   int rc = ensure();
   if (rc != F16_OK) return rc;
   if (N < 0 || (N > 0 && (!xu_soa || !xdot_soa)) || ld_in < N || ld_out < N) { set_err("Nlplant_batch_dev: bad argument"); return F16_ERR_ARG; }
-  CK(DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(fi, fi_default, xcg, xcg_default), xu_soa,
-              ld_in, xdot_soa, ld_out, N, status));
+  CK(run_nlplant(sel_of(fi, fi_default, xcg, xcg_default), xu_soa, ld_in, xdot_soa, ld_out, N, status));
   return F16_OK;
 }
 
@@ -359,8 +380,7 @@ int calc_xdot_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
   int rc = ensure();
   if (rc != F16_OK) return rc;
   if (N < 0 || (N > 0 && (!x_soa || !u_soa || !xdot_soa)) || ld_x < N || ld_u < N || ld_out < N) { set_err("calc_xdot_batch_dev: bad argument"); return F16_ERR_ARG; }
-  CK(DISPATCH(launch_calc_xdot, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa,
-              ld_x, u_soa, ld_u, xdot_soa, ld_out, N, status));
+  CK(run_calc_xdot(sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, xdot_soa, ld_out, N, status));
   return F16_OK;
 }
 
@@ -473,8 +493,8 @@ int Nlplant_batch(const double* xu_soa, double* xdot_soa, const unsigned char* f
   const double* d_xcg;
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, xu_soa, 17 * n * 8);
-  CK(DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
-              (const double*)G.b_in.p, N, (double*)G.b_out.p, N, N, (int*)G.b_st.p));
+  CK(run_nlplant(sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p, N, (double*)G.b_out.p, N, N,
+                 (int*)G.b_st.p));
   D2H(xdot_soa, G.b_out.p, 18 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);
   CK(cudaStreamSynchronize(G.stream));
@@ -498,8 +518,8 @@ int calc_xdot_batch(const double* x_soa, const double* u_soa, double* xdot_soa, 
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, x_soa, 18 * n * 8);
   H2D(G.b_in2.p, u_soa, 4 * n * 8);
-  CK(DISPATCH(launch_calc_xdot, cfg(G.smem_tables && N >= 4096), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
-              (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N, (double*)G.b_out.p, N, N, (int*)G.b_st.p));
+  CK(run_calc_xdot(sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N,
+                   (double*)G.b_out.p, N, N, (int*)G.b_st.p));
   D2H(xdot_soa, G.b_out.p, 18 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);
   CK(cudaStreamSynchronize(G.stream));

@@ -319,12 +319,34 @@ F16_FD void clip_commands(const double (&u)[4], double (&uc)[4]) {
   uc[3] = clipd(u[3], -30, 30);
 }
 
+// rows 12..17 of Nlplant's output (nlplant.c:445-450): accels (:512-552, grav = 32.174 and the unclamped velocity v6), then
+// mach = vt / sqrt(1.4 * 1716.3 * temp), qbar, ps = 1715 rho temp (:479-485) from the clamped vt.  xd[6..8] are read.
+F16_FD void nlplant_extra_rows(double v6, double vt, double sa, double ca, double sb, double cb, double st, double ct,
+                               double sphi, double cphi, double P, double Q, double R, double qbar, double hrho, double temp,
+                               double inv_temp, double (&xd)[18]) {
+  const double inv_grav = 1.0 / 32.174;
+  const double vcb = v6 * cb;
+  const double vel_u = vcb * ca, vel_v = v6 * sb, vel_w = vcb * sa;
+  const double u_dot = fma(cb * ca, xd[6], -fma(vel_v * ca, xd[8], vel_w * xd[7]));
+  const double v_dot = fma(sb, xd[6], vcb * xd[8]);
+  const double w_dot = fma(cb * sa, xd[6], fma(vel_u, xd[7], -(vel_v * sa) * xd[8]));
+  xd[12] = fma(inv_grav, fma(Q, vel_w, fma(-R, vel_v, u_dot)), st);
+  xd[13] = fma(inv_grav, fma(R, vel_u, fma(-P, vel_w, v_dot)), -(ct * sphi));
+  xd[14] = fma(-inv_grav, fma(P, vel_v, fma(-Q, vel_u, w_dot)), ct * cphi);
+  xd[15] = vt * sqrt(inv_temp * (1.0 / (1.4 * 1716.3)));
+  xd[16] = qbar;
+  const double ps = (3430.0 * hrho) * temp;  // hrho = 0.5 rho
+  xd[17] = ps == 0.0 ? 1715.0 : ps;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // env.py::_calc_xdot (env.py:65-103) for the hifi model, all 18 derivatives.  `img` is the fast image, `uc` the
 // saturated commands.  Precondition (checked by the caller through step_ok): states inside parameters.py bounds,
 // no NaN.  Returns false when alpha / beta leave the hifi tables (the caller then reports the exact status word).
 // ------------------------------------------------------------------------------------------------------
-template <bool LIBM_TRIG>
+// NLP = true turns the function into Nlplant itself (nlplant.c:23-457): x[0..16] is xu (x[16] the flap angle, x[17] unused),
+// `uc` is not read, and rows 12..17 are nx, ny, nz (accels, nlplant.c:512-552), mach, qbar, ps instead of the actuator rows.
+template <bool LIBM_TRIG, bool NLP = false>
 F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
   const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
 
@@ -363,7 +385,8 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   // atmos, nlplant.c:467-490: only qbar (Nlplant) and qbar/ps (upd_lef, utils.py:291-296) are consumed here
   const double tfac = fma(K.tlapse, x[2], 1.0);
   const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
-  const double qbar = half_rho(img, tfac) * (vt * vt);
+  const double hrho = half_rho(img, tfac);
+  const double qbar = hrho * (vt * vt);
   // one reciprocal for 1/(vt cb), 1/vt, 1/ct and 1/temp
   const double vc = vt * cb, tc = ct * temp;
   const double rr = rcp_nr(vc * tc);
@@ -491,6 +514,10 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * fma(P, P, -(R * R))));
   xd[11] = fma(K.izz_n, N_tot, fma(K.izz_l, L_tot, fma(K.izz_pq, PQ, K.izz_qr * QR)));
 
+  if (NLP) {  // accels (grav = 32.174, the UNCLAMPED x[6]) and the three atmosphere outputs, nlplant.c:445-450,467-490,512-552
+    nlplant_extra_rows(x[6], vt, sa, ca, sb, cb, st, ct, sphi, cphi, P, Q, R, qbar, hrho, temp, inv_temp, xd);
+    return true;
+  }
   // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
@@ -582,7 +609,7 @@ F16_FD double lrow(const double* row, const LofiA& A) {
   return fma(A.ada, row[A.L] - lo, lo);
 }
 
-template <bool LIBM_TRIG>
+template <bool LIBM_TRIG, bool NLP = false>
 F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
   const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
   const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
@@ -615,7 +642,8 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
   const double tfac = fma(K.tlapse, x[2], 1.0);
   const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
-  const double qbar = half_rho(img + F16_IMG_LOFI_DOUBLES - F16_FI_POW, tfac) * (vt * vt);
+  const double hrho = half_rho(img + F16_IMG_LOFI_DOUBLES - F16_FI_POW, tfac);
+  const double qbar = hrho * (vt * vt);
   const double vc = vt * cb, tc = ct * temp;
   const double rr = rcp_nr(vc * tc);
   const double inv_vc = rr * tc, inv_tc = rr * vc;
@@ -735,6 +763,10 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   xd[10] = fma(K.inv_Jy, M_tot, fma(K.iyy_pr, P * R, K.iyy_p2 * fma(P, P, -(R * R))));
   xd[11] = fma(K.izz_n, N_tot, fma(K.izz_l, L_tot, fma(K.izz_pq, PQ, K.izz_qr * QR)));
 
+  if (NLP) {
+    nlplant_extra_rows(x[6], vt, sa, ca, sb, cb, st, ct, sphi, cphi, P, Q, R, qbar, hrho, temp, inv_temp, xd);
+    return true;
+  }
   // actuators and leading-edge flap, utils.py:289-330 (the flap states evolve in the lofi model too; Nlplant ignores them)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;

@@ -67,6 +67,9 @@ cudaError_t launch_trim_fast(const LaunchCfg&, const DevTables&, const BatchSel&
 cudaError_t launch_step_lofi_fast(const LaunchCfg&, const DevTables&, const BatchSel&, double* x, long long ld_x,
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done);
+// Nlplant_batch (u == nullptr, x = xu [17][N]) / calc_xdot_batch on the arithmetic of f16_fast.cuh, TMA-staged input tiles
+cudaError_t launch_xdot_fast(const LaunchCfg&, const DevTables&, const BatchSel&, const double* x, long long ld_x, const double* u,
+                             long long ld_u, double* xdot, long long ld_out, long long N, int* status, unsigned* redo);
 cudaError_t launch_fast_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta, const double* el,
                               long long N, double* coef, int* cells, double* lam, int* status);
 }

@@ -2,6 +2,10 @@
 // Compiled with -fmad=false: every fused multiply-add in this kernel is an explicit fma() in the source, so the
 // result does not depend on which mul/add pairs ptxas would have chosen to contract in a given instantiation
 // (CTA size, table staging) -- all variants of the kernel, and the host emulation of the tests, agree bit for bit.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "f16_kernels_common.cuh"
 #include "f16_fast.cuh"
 
@@ -199,6 +203,302 @@ cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const 
                              ld_x, info, ld_info, status);
   return launch_persistent(cfg, trim_fast_kernel<0>, 256, F16_LOFI_STEP_IMG_DOUBLES * 8, N, 256, tabs, sel, h, v, N, tol, maxiter,
                            g, x_trim, ld_x, info, ld_info, status);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Nlplant_batch / calc_xdot_batch, F16_MATH_FAST: one evaluation per aircraft on the arithmetic of f16_fast.cuh.
+//
+// These launches move 284 / 324 B per aircraft for ~480 FP64 instructions: HBM-bound.  Layout of the work:
+//   * a warp-task is 32 consecutive aircraft (one 256-byte run of every SoA plane); task t goes to warp slot
+//     t mod (12 warps x grid), slots numbered warp-major (slot = warp * grid + cta), so a partial last round is spread
+//     over all SMs instead of filling some CTAs and leaving the others idle;
+//   * input: the SoA arrays are described to the TMA unit as 2-D tensors (planes x aircraft, CUtensorMap), and the 18 + 4
+//     (17) plane runs of a task arrive as ONE box each (cp.async.bulk.tensor.2d, issued by one lane: 22 separate 256-byte
+//     bulk copies cost 340 instructions per task in address arithmetic and uniform-register moves, a third of the kernel)
+//     in the warp's own 5.5 KB shared buffer, completing on the warp's own mbarrier; a box that sticks out of the batch is
+//     zero-filled by the hardware, so the ragged last task needs no special case.  The boxes of the warp's NEXT task are
+//     requested as soon as the current values are in registers, so they fly during the arithmetic and the stores of the
+//     current one; the first task's boxes are requested before the CTA waits for its table image;
+//   * tables: the (f, d) image in shared memory (155 KB hifi / 7 KB lofi), one CTA of 384 threads per SM;
+//   * output: 18 coalesced 8-byte stores per lane straight from registers (a shared output tile does not fit beside the
+//     image).
+// An aircraft outside the preconditions of the fast arithmetic (a NaN anywhere, altitude outside the density table, an angle
+// beyond 2^30 rad, alpha / beta / elevator outside the tables) takes the reference-order evaluation on the standard image in
+// global memory, which also produces the exact status word.  Pointers that are not 16-byte aligned or an odd plane stride
+// (a tensor map needs 16-byte strides) fall back to plain loads.
+// ------------------------------------------------------------------------------------------------------
+
+template <int FI, bool NLP, int THREADS>
+struct XfSmem {
+  static constexpr int XF_WARPS = THREADS / 32;
+  static constexpr int NPL = NLP ? 17 : 22;
+  static constexpr int IMG_BYTES = FI ? F16_FI_BYTES : F16_LOFI_STEP_IMG_DOUBLES * 8;
+  static constexpr int IMG_PAD = (IMG_BYTES + 127) / 128 * 128;
+  static constexpr int BUF_DOUBLES = NPL * 32;
+  static constexpr int BARS = IMG_PAD + XF_WARPS * BUF_DOUBLES * 8;
+  static constexpr int TOTAL = BARS + (1 + XF_WARPS) * 8;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, int bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap* map, int col, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(col), "r"(0), "r"(bar)
+               : "memory");
+}
+
+// rare path: the reference-order evaluation (f16_model.cuh) on the standard image in global memory
+template <int FI, bool NLP>
+static __device__ __noinline__ unsigned xdot_reference_order(const double* img_std, const double* x_, const double* u_, double xcg,
+                                                             double* xd_) {
+  double xd[18];
+  unsigned st;
+  if (NLP) {
+    double xu[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) xu[i] = x_[i];
+    st = nlplant_eval<FI>(img_std, xu, xcg, xd);
+  } else {
+    double x[18], u[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = x_[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = u_[i];
+    st = calc_xdot<FI>(img_std, x, u, xcg, xd);
+  }
+#pragma unroll
+  for (int i = 0; i < 18; i++) xd_[i] = xd[i];
+  return st;
+}
+
+// The marked aircraft of a warp's tasks: reference-order evaluation on the standard image in global memory (also the exact
+// status word).  A function of its own, called once after the main loop, so that its registers, its call and its local
+// arrays do not take part in the register allocation of that loop.
+template <int FI, bool NLP>
+static __device__ __noinline__ void xdot_redo_pass(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x,
+                                                   const double* __restrict__ u_g, long long ld_u, double* __restrict__ xd_g,
+                                                   long long ld_out, int* __restrict__ status, const unsigned* redo, long long t,
+                                                   long long stride, long long tiles, int lane) {
+  constexpr int NX = NLP ? 17 : 18;
+#pragma unroll 1
+  for (; t < tiles; t += stride) {
+    const unsigned later = redo[t];
+    if (!((later >> lane) & 1u)) continue;
+    const long long n = (t << 5) + lane;
+    double xs[18], us[4], xo[18];
+#pragma unroll
+    for (int i = 0; i < NX; i++) xs[i] = x_g[i * ld_x + n];
+    if (NLP) xs[17] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) us[i] = NLP ? 0.0 : u_g[i * ld_u + n];
+    const unsigned st = xdot_reference_order<FI, NLP>(FI ? tabs.hifi : tabs.lofi, xs, us, sel.xcg ? sel.xcg[n] : sel.xcg_default, xo);
+#pragma unroll
+    for (int i = 0; i < 18; i++) xd_g[i * ld_out + n] = st ? qnan() : xo[i];
+    if (status) status[n] = (int)st;
+  }
+}
+
+template <int FI, bool NLP, int THREADS>
+__global__ void __maxnreg__(65536 / THREADS / 8 * 8 > 255 ? 255 : 65536 / THREADS / 8 * 8)
+xdot_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_u,
+                 const double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g, long long ld_u,
+                 double* __restrict__ xd_g, long long ld_out, long long N, int* __restrict__ status, int bulk_ok,
+                 unsigned* __restrict__ redo) {
+  using S = XfSmem<FI, NLP, THREADS>;
+  constexpr int NX = NLP ? 17 : 18, NU = NLP ? 0 : 4, XF_WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* img = reinterpret_cast<const double*>(f16_smem);
+  double* buf = reinterpret_cast<double*>(f16_smem + S::IMG_PAD) + warp * S::BUF_DOUBLES;
+  const uint32_t bar_tab = smem_u32(f16_smem + S::BARS), bar_w = bar_tab + 8 * (1 + warp), buf_a = smem_u32(buf);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= XF_WARPS; i++) mbar_init(bar_tab + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // table image: global -> shared, completes on bar_tab
+    mbar_expect_tx(bar_tab, S::IMG_BYTES);
+    if (FI) {
+      constexpr int CHUNK = 32768;
+#pragma unroll 1
+      for (int off = 0; off < S::IMG_BYTES; off += CHUNK)
+        bulk_g2s(smem_u32(f16_smem + off), reinterpret_cast<const char*>(tabs.hifi_fast) + off,
+                 (S::IMG_BYTES - off) < CHUNK ? (S::IMG_BYTES - off) : CHUNK, bar_tab);
+    } else {  // lofi step image = the lofi tables + the centre table of half_rho
+      bulk_g2s(smem_u32(f16_smem), tabs.lofi, F16_IMG_LOFI_BYTES, bar_tab);
+      bulk_g2s(smem_u32(f16_smem + F16_IMG_LOFI_BYTES), tabs.hifi_fast + F16_FI_POW, 2 * F16_FI_NPOW * 8, bar_tab);
+    }
+  }
+  const long long tiles = (N + 31) >> 5;
+  const long long stride = (long long)XF_WARPS * gridDim.x;
+  long long t = (long long)warp * gridDim.x + blockIdx.x;
+
+  auto issue = [&](long long tile) {  // the whole warp, converged
+    if (!bulk_ok || tile >= tiles) return;
+    if (lane == 0) {
+      const int col = (int)(tile << 5);  // tensor coordinates are 32-bit: launch_xdot_fast keeps N below 2^31 on this path
+      mbar_expect_tx(bar_w, S::NPL * 256);
+      tma_box_g2s(buf_a, &map_x, col, bar_w);
+      if (NU) tma_box_g2s(buf_a + NX * 256, &map_u, col, bar_w);
+    }
+  };
+  issue(t);
+  mbar_wait(bar_tab, 0);
+  uint32_t phase = 0;
+  unsigned any_later = 0;
+  for (; t < tiles; t += stride) {
+    const long long n = (t << 5) + lane;
+    const bool staged = bulk_ok != 0;
+    double x[18], u[4];
+    if (staged) {
+      mbar_wait(bar_w, phase);
+      phase ^= 1;
+#pragma unroll
+      for (int i = 0; i < NX; i++) x[i] = buf[i * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < NU; i++) u[i] = buf[(NX + i) * 32 + lane];
+      __syncwarp();
+      // the reads above (generic proxy) are ordered before the next task's bulk copies (async proxy) into the same buffer
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else {
+      const long long m = n < N ? n : N - 1;
+#pragma unroll
+      for (int i = 0; i < NX; i++) x[i] = x_g[i * ld_x + m];
+#pragma unroll
+      for (int i = 0; i < NU; i++) u[i] = u_g[i * ld_u + m];
+    }
+    if (NLP) x[17] = 0.0;
+    issue(t + stride);
+    // A lane that cannot take the fast arithmetic is only MARKED here (one 4-byte word per task) and evaluated after the loop:
+    // the reference-order function is a call, and a call inside this loop makes every value that is live across it a spill
+    // (measured: 17 local loads per task; 255 registers instead of 168 to get rid of them).
+    const int own = n < N ? owns<FI>(sel, n) : 0;
+    bool ok = false;
+    if (own == 1) {
+      const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+      ok = (x[2] >= -4000.0) & (x[2] <= 102000.0) & fastmath::small_angle(x[3]) & fastmath::small_angle(x[4]) &
+           fastmath::small_angle(x[5]);
+      ok &= !either_nan(x[0], x[1]) & !either_nan(x[6], x[9]) & !either_nan(x[10], x[11]) & !either_nan(x[12], x[14]) &
+            !either_nan(x[15], x[16]);
+      if (FI) ok &= (fabs(x[13]) <= 25.0);
+      else ok &= fastmath::small_angle(x[7]) & !either_nan(x[13], x[13]);
+      double uc[4] = {0.0, 0.0, 0.0, 0.0};
+      if (!NLP) {
+        ok &= !either_nan(u[0], u[1]) & !either_nan(u[2], u[3]) & !either_nan(x[17], x[17]);
+        fastmath::clip_commands(u, uc);
+      }
+      if (ok) {
+        double xd[18];
+        ok = FI ? fastmath::calc_xdot_hifi<false, NLP>(img, x, uc, xcg, xd) : fastmath::calc_xdot_lofi<false, NLP>(img, x, uc, xcg, xd);
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 18; i++) xd_g[i * ld_out + n] = xd[i];
+          if (status) status[n] = 0;
+        }
+      }
+    } else if (own < 0) {  // a fidelity flag that is neither 0 nor 1: reported by the hifi launch
+#pragma unroll
+      for (int i = 0; i < 18; i++) xd_g[i * ld_out + n] = qnan();
+      if (status) status[n] = (int)ST_FIDELITY;
+    }
+    const unsigned later = __ballot_sync(0xffffffffu, own == 1 && !ok);
+    if (lane == 0) redo[t] = later;  // always (4 bytes per task): the pass below reads only words of this launch
+    any_later |= later;
+  }
+  if (!any_later) return;  // warp-uniform, and the common case
+  __syncwarp();            // lane 0's redo[] stores are visible to the other lanes of its warp
+  xdot_redo_pass<FI, NLP>(tabs, sel, x_g, ld_x, u_g, ld_u, xd_g, ld_out, status, redo, (long long)warp * gridDim.x + blockIdx.x, stride,
+                          tiles, lane);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// SoA array [planes][ld] of doubles, N valid columns, as a 2-D tensor with boxes of `planes` x 32 aircraft
+static bool soa_tensor_map(CUtensorMap* m, const double* base, long long ld, long long N, int planes) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1) || N >= (1LL << 31) || N < 1) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)planes};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  const cuuint32_t box[2] = {32, (cuuint32_t)planes};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int FI, bool NLP>
+static cudaError_t launch_xdot_fast_one(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* x,
+                                        long long ld_x, const double* u, long long ld_u, double* xd, long long ld_out, long long N,
+                                        int* status, unsigned* redo) {
+  CUtensorMap mx, mu;
+  memset(&mx, 0, sizeof mx);
+  memset(&mu, 0, sizeof mu);
+  bool tma = soa_tensor_map(&mx, x, ld_x, N, NLP ? 17 : 18);
+  if (tma && !NLP) tma = soa_tensor_map(&mu, u, ld_u, N, 4);
+  // CTA size: what keeps the main loop free of spills (measured at 2^20 aircraft, hifi): Nlplant 384 threads / 168 registers
+  // 61 us, calc_xdot (22 input values instead of 17) 256 threads / 255 registers 68 us against 76 us at 384.  F16_XF_THREADS
+  // overrides for experiments.
+  static const int forced = getenv("F16_XF_THREADS") ? atoi(getenv("F16_XF_THREADS")) : 0;
+  const int threads = forced ? forced : (NLP ? 384 : 256);
+  if (threads == 256)
+    return launch_persistent(cfg, xdot_fast_kernel<FI, NLP, 256>, 256, XfSmem<FI, NLP, 256>::TOTAL, N, 256, tabs, sel, mx, mu, x, ld_x, u,
+                             ld_u, xd, ld_out, N, status, tma ? 1 : 0, redo);
+  return launch_persistent(cfg, xdot_fast_kernel<FI, NLP, 384>, 384, XfSmem<FI, NLP, 384>::TOTAL, N, 384, tabs, sel, mx, mu, x, ld_x, u,
+                           ld_u, xd, ld_out, N, status, tma ? 1 : 0, redo);
+}
+
+static bool sel_wants(const BatchSel& s, int FI) { return s.fi != nullptr || s.fi_default == FI || (FI == 1 && s.fi_default != 0); }
+
+// u == nullptr: Nlplant_batch (x is xu [17][N]); else calc_xdot_batch
+// redo: device scratch of one unsigned per 32 aircraft (which lanes of a task take the reference-order path)
+cudaError_t launch_xdot_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* x, long long ld_x,
+                             const double* u, long long ld_u, double* xd, long long ld_out, long long N, int* status, unsigned* redo) {
+  if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (sel_wants(sel, 1))
+    e = u ? launch_xdot_fast_one<1, false>(cfg, tabs, sel, x, ld_x, u, ld_u, xd, ld_out, N, status, redo)
+          : launch_xdot_fast_one<1, true>(cfg, tabs, sel, x, ld_x, nullptr, 0, xd, ld_out, N, status, redo);
+  if (e == cudaSuccess && sel_wants(sel, 0))
+    e = u ? launch_xdot_fast_one<0, false>(cfg, tabs, sel, x, ld_x, u, ld_u, xd, ld_out, N, status, redo)
+          : launch_xdot_fast_one<0, true>(cfg, tabs, sel, x, ld_x, nullptr, 0, xd, ld_out, N, status, redo);
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -264,6 +264,46 @@ def test_nlplant_batch_mixed_fidelity_and_xcg(f16, oracle):
     assert st[5] == 1 << 22 and np.isnan(out[:, 5]).all() and not st[6]
 
 
+@pytest.mark.parametrize("fi", [1, 0])
+def test_oneshot_fast_kernels_load_paths_agree(f16, fi):
+    """The F16_MATH_FAST one-shot kernels fetch full, 16-byte-aligned tasks of 32 aircraft by TMA bulk copies and everything
+    else (odd N / odd plane stride, ragged last task) by plain loads: every path must give the same bits, for
+    Nlplant_batch and calc_xdot_batch, with status words, NaN inputs and out-of-table aircraft in the batch."""
+    prev = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        n = 6000
+        xu = random_envelope_xu(n, seed=77, hifi=bool(fi))
+        r = np.random.default_rng(78)
+        x = np.vstack([xu, r.uniform(-30, 30, (1, n))])
+        u = np.stack([r.uniform(500, 20000, n), r.uniform(-30, 30, n), r.uniform(-25, 25, n), r.uniform(-35, 35, n)])
+        x[7, 5] = np.deg2rad(60.0)      # outside the hifi tables (lofi: fine)
+        x[8, 6] = np.deg2rad(-31.0)     # outside both
+        x[9, 7] = np.nan                # NaN in a rate: reference-order path, NaN derivatives, status 0
+        x[2, 8] = 120000.0              # altitude beyond the density table of the fast arithmetic (tfac = 0.156)
+        x[4, 9] = 4.0e9                 # Euler angle beyond 2^30
+        fb = f16.F16Batch(x, u, fi_flag=fi, xcg=0.3)
+        full = fb._calc_xdot(x, u)
+        full_st = fb.last_status.copy()
+        nl, nl_st = f16.nlplant(x[:17], fi, 0.3)
+        assert full_st[6] == 1 << 19 and (full_st[5] == (1 << 18 if fi else 0)) and full_st[7] == 0 and np.isnan(full[9:12, 7]).all()
+        assert np.isfinite(full[:, 8]).all() and np.isfinite(full[:, 9]).all() and np.isfinite(full[:, 10:]).all()
+        for m in (4096, 4098, 4099, 4127, 5001):
+            fbm = f16.F16Batch(x[:, :m], u[:, :m], fi_flag=fi, xcg=0.3)
+            out = fbm._calc_xdot(np.ascontiguousarray(x[:, :m]), np.ascontiguousarray(u[:, :m]))
+            assert np.array_equal(out, full[:, :m], equal_nan=True), m
+            assert np.array_equal(fbm.last_status, full_st[:m]), m
+            o2, s2 = f16.nlplant(np.ascontiguousarray(x[:17, :m]), fi, 0.3)
+            assert np.array_equal(o2, nl[:, :m], equal_nan=True) and np.array_equal(s2, nl_st[:m]), m
+        # the small-batch path (tables through L2, f16_model.cuh arithmetic) agrees to the derivative tolerance
+        small = f16.F16Batch(x[:, :1000], u[:, :1000], fi_flag=fi, xcg=0.3)._calc_xdot(np.ascontiguousarray(x[:, :1000]),
+                                                                                     np.ascontiguousarray(u[:, :1000]))
+        ok = full_st[:1000] == 0
+        fin = np.isfinite(full[:, :1000]).all(axis=0) & ok
+        assert scaled_err(small[:, fin], full[:, :1000][:, fin]) < TOL_DERIV
+    finally:
+        f16.lib.f16_set_math_mode(prev)
+
+
 def test_nlplant_batch_edges(f16):
     out, st = f16.nlplant(np.zeros((17, 0)))
     assert out.shape == (18, 0)
