@@ -228,6 +228,9 @@ cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const 
 // (a tensor map needs 16-byte strides) fall back to plain loads.
 // ------------------------------------------------------------------------------------------------------
 
+#ifndef XF_TABLE_CHUNK
+#define XF_TABLE_CHUNK 8192
+#endif
 template <int FI, bool NLP, int THREADS>
 struct XfSmem {
   static constexpr int XF_WARPS = THREADS / 32;
@@ -340,11 +343,17 @@ xdot_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorM
   if (threadIdx.x == 0) {  // table image: global -> shared, completes on bar_tab
     mbar_expect_tx(bar_tab, S::IMG_BYTES);
     if (FI) {
-      constexpr int CHUNK = 32768;
+      // every CTA of the grid reads the same 155 KB at the same moment: each starts at a different chunk, so that at any time
+      // the requests of the 148 SMs are spread over the L2 slices instead of queueing at the few that hold "the current" chunk
+      constexpr int CHUNK = XF_TABLE_CHUNK, NCHUNK = (S::IMG_BYTES + CHUNK - 1) / CHUNK;
+      int c = (int)(blockIdx.x % NCHUNK);
 #pragma unroll 1
-      for (int off = 0; off < S::IMG_BYTES; off += CHUNK)
+      for (int k = 0; k < NCHUNK; k++) {
+        const int off = c * CHUNK;
         bulk_g2s(smem_u32(f16_smem + off), reinterpret_cast<const char*>(tabs.hifi_fast) + off,
                  (S::IMG_BYTES - off) < CHUNK ? (S::IMG_BYTES - off) : CHUNK, bar_tab);
+        c = c + 1 == NCHUNK ? 0 : c + 1;
+      }
     } else {  // lofi step image = the lofi tables + the centre table of half_rho
       bulk_g2s(smem_u32(f16_smem), tabs.lofi, F16_IMG_LOFI_BYTES, bar_tab);
       bulk_g2s(smem_u32(f16_smem + F16_IMG_LOFI_BYTES), tabs.hifi_fast + F16_FI_POW, 2 * F16_FI_NPOW * 8, bar_tab);
