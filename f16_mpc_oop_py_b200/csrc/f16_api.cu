@@ -152,7 +152,7 @@ int init_locked(const char* table_path, int device) {
   if (const char* v = getenv("F16_CLR")) G.clr_mode = (!strcmp(v, "file") || !strcmp(v, "1")) ? F16_CLR_FROM_FILE : F16_CLR_AS_BUILT;
   if (const char* v = getenv("F16_STEP_THREADS")) G.step_threads = atoi(v);
   if (const char* v = getenv("F16_TABLE_STAGING")) G.smem_tables = atoi(v) != 0;
-  if (const char* v = getenv("F16_LIN_VARIANT")) G.lin_variant = atoi(v) == 1 ? 1 : 0;
+  if (const char* v = getenv("F16_LIN_VARIANT")) G.lin_variant = (atoi(v) == 1 || atoi(v) == 2) ? atoi(v) : 0;
 
   int rc = upload_tables();
   if (rc != F16_OK) return G.init_rc = rc;
@@ -210,6 +210,19 @@ cudaError_t run_nlplant(const f16::BatchSel& sel, const double* xu, long long ld
     return f16::fast::launch_xdot_fast(cfg(true), tabs(), sel, xu, ld_in, nullptr, 0, xdot, ld_out, N, status, (unsigned*)G.b_redo.p);
   }
   return DISPATCH(launch_nlplant, cfg(G.smem_tables && N >= 4096), tabs(), sel, xu, ld_in, xdot, ld_out, N, status);
+}
+// linearise_batch.  F16_MATH_STRICT: the staged reference-order kernels (variant 0 / 2: CTA per 32 aircraft, 1: warp per
+// aircraft).  F16_MATH_FAST, variant 0: the two-aircraft-per-warp kernel on the arithmetic of f16_fast.cuh
+// (f16_linearise_fast.cu); variants 1 and 2 keep the strict kernels in fast mode as well.
+cudaError_t run_linearise(const f16::BatchSel& sel, const double* x, long long ld_x, const double* u, long long ld_u, long long N,
+                          double eps, int scheme, double* A, double* B, int* status) {
+  if (G.math_mode == F16_MATH_FAST && G.lin_variant == 0 && N < (1LL << 31)) {
+    cudaError_t e = G.b_redo.reserve((size_t)((N + 1) / 2) * 4);
+    if (e != cudaSuccess) return e;
+    return f16::fast::launch_linearise_fast(cfg(true), tabs(), sel, x, ld_x, u, ld_u, N, eps, scheme, A, B, status,
+                                            (unsigned*)G.b_redo.p);
+  }
+  return f16::strict::launch_linearise(cfg(true), tabs(), sel, x, ld_x, u, ld_u, N, eps, scheme, A, B, status);
 }
 cudaError_t run_calc_xdot(const f16::BatchSel& sel, const double* x, long long ld_x, const double* u, long long ld_u, double* xdot,
                           long long ld_out, long long N, int* status) {
@@ -296,7 +309,7 @@ int f16_set_step_threads(int threads) {
 int f16_set_linearise_variant(int variant) {
   std::lock_guard<std::mutex> lk(G_mu);
   int prev = G.lin_variant;
-  G.lin_variant = variant == 1 ? 1 : 0;
+  G.lin_variant = (variant == 1 || variant == 2) ? variant : 0;
   return prev;
 }
 
@@ -468,9 +481,7 @@ int linearise_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
     set_err("linearise_batch_dev: bad argument");
     return F16_ERR_ARG;
   }
-  // always the strict build: the difference quotient multiplies rounding noise by 1/eps (1e5)
-  CK(f16::strict::launch_linearise(cfg(true), tabs(), sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u,
-                                   N, eps, scheme, A, B, status));
+  CK(run_linearise(sel_of(fi, fi_default, xcg, xcg_default), x_soa, ld_x, u_soa, ld_u, N, eps, scheme, A, B, status));
   return F16_OK;
 }
 
@@ -631,10 +642,8 @@ int linearise_batch(const double* x_soa, const double* u_soa, long long N, doubl
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, x_soa, 18 * n * 8);
   H2D(G.b_in2.p, u_soa, 4 * n * 8);
-  // always the strict build: the difference quotient multiplies rounding noise by 1/eps (1e5)
-  CK(f16::strict::launch_linearise(cfg(true), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default),
-                                   (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, eps, scheme,
-                                   (double*)G.b_a.p, (double*)G.b_b.p, (int*)G.b_st.p));
+  CK(run_linearise(sel_of(d_fi, fi_default, d_xcg, xcg_default), (const double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, eps,
+                   scheme, (double*)G.b_a.p, (double*)G.b_b.p, (int*)G.b_st.p));
   D2H(A, G.b_a.p, 324 * n * 8);
   D2H(B, G.b_b.p, 72 * n * 8);
   if (status) D2H(status, G.b_st.p, n * 4);

@@ -137,7 +137,7 @@ F16_FD void sincos_any(double x, double& s, double& c) {
 }
 
 #if defined(__CUDACC__)
-__device__ __noinline__ void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
+static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
 #else
 static void sincos_libm(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 #endif
@@ -255,6 +255,19 @@ F16_FD bool step_ok(const double (&x)[18]) {
   return ok;
 }
 
+// Preconditions of calc_xdot_hifi / calc_xdot_lofi on a state that did NOT pass the step bounds (one-shot kernels, linearise):
+// no NaN in x[0..16], altitude inside the density table of half_rho (tfac in [0.28, 1.03)), Euler angles (lofi: alpha too)
+// below 2^30 rad for reduce_pio2, and for hifi the elevator inside its table (calc_xdot_hifi itself checks alpha and beta).
+template <int FI>
+F16_FD bool fast_ok(const double (&x)[18]) {
+  bool ok = (x[2] >= -4000.0) & (x[2] <= 102000.0) & small_angle(x[3]) & small_angle(x[4]) & small_angle(x[5]);
+  ok &= !either_nan(x[0], x[1]) & !either_nan(x[6], x[9]) & !either_nan(x[10], x[11]) & !either_nan(x[12], x[14]) &
+        !either_nan(x[15], x[16]);
+  if (FI) ok &= (fabs(x[13]) <= 25.0);
+  else ok &= small_angle(x[7]) & !either_nan(x[13], x[13]);
+  return ok;
+}
+
 // The closed-loop law of f16_lqr_t scattered to state order by the host (make_dense_law): every selected state is a
 // compile-time register here, columns that carry no gain are skipped by warp-uniform branches on `colmask`.
 //     u[r] = u0[r] - extra[r] - sum_i Kf[i][r] (x[i] - xr[i])        for rows in row_mask
@@ -319,6 +332,30 @@ F16_FD void clip_commands(const double (&u)[4], double (&uc)[4]) {
   uc[3] = clipd(u[3], -30, 30);
 }
 
+// rows 12..17 of _calc_xdot: actuator lags and the leading-edge-flap schedule, utils.py:289-330.  atmos_out = 9.05 qbar / ps of
+// atmos(alt, x[6]) and alpha_deg come from the caller (calc_xdot_hifi / _lofi compute them from their shared reciprocal).
+F16_FD void actuator_rows(const double (&x)[18], const double (&uc)[4], double atmos_out, double alpha_deg, double (&xd)[18]) {
+  const double lf_in = fma(2.0, alpha_deg, x[17]);
+  // flap command saturation (utils.py:297): active in ordinary flight (the trim flap angle is 0.4 deg), so a select
+  const double lef_cmd = clipd(fma(lf_in, K.c1_38, K.c1_45) - atmos_out, 0, 25);
+  const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
+               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_cmd - x[16]);
+  xd[12] = r12;
+  xd[13] = r13;
+  xd[14] = r14;
+  xd[15] = r15;
+  xd[16] = r16;
+  // rate limits (utils.py:299-330) only cost selects when one of them is active (or a value is NaN)
+  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
+    xd[12] = clipd(r12, -10000, 10000);
+    xd[13] = clipd(r13, -60, 60);
+    xd[14] = clipd(r14, -80, 80);
+    xd[15] = clipd(r15, -120, 120);
+    xd[16] = clipd(r16, -25, 25);
+  }
+  xd[17] = (alpha_deg - lf_in) * 7.25;
+}
+
 // rows 12..17 of Nlplant's output (nlplant.c:445-450): accels (:512-552, grav = 32.174 and the unclamped velocity v6), then
 // mach = vt / sqrt(1.4 * 1716.3 * temp), qbar, ps = 1715 rho temp (:479-485) from the clamped vt.  xd[6..8] are read.
 F16_FD void nlplant_extra_rows(double v6, double vt, double sa, double ca, double sb, double cb, double st, double ct,
@@ -346,8 +383,11 @@ F16_FD void nlplant_extra_rows(double v6, double vt, double sa, double ca, doubl
 // ------------------------------------------------------------------------------------------------------
 // NLP = true turns the function into Nlplant itself (nlplant.c:23-457): x[0..16] is xu (x[16] the flap angle, x[17] unused),
 // `uc` is not read, and rows 12..17 are nx, ny, nz (accels, nlplant.c:512-552), mach, qbar, ps instead of the actuator rows.
-template <bool LIBM_TRIG, bool NLP = false>
-F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
+// AUX = true also returns aux = {qbar/ps term of the flap schedule, alpha in degrees}: what actuator_rows() needs to re-evaluate
+// rows 12..17 alone (linearise: the columns lf1 and the four inputs reach f through those rows only).
+template <bool LIBM_TRIG, bool NLP = false, bool AUX = false>
+F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18],
+                           double* aux = nullptr) {
   const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
 
   const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
@@ -521,25 +561,8 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
-  const double lf_in = fma(2.0, alpha_deg, x[17]);
-  // flap command saturation (utils.py:297): active in ordinary flight (the trim flap angle is 0.4 deg), so a select
-  const double lef_cmd = clipd(fma(lf_in, K.c1_38, K.c1_45) - atmos_out, 0, 25);
-  const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
-               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_cmd - x[16]);
-  xd[12] = r12;
-  xd[13] = r13;
-  xd[14] = r14;
-  xd[15] = r15;
-  xd[16] = r16;
-  // rate limits (utils.py:299-330) only cost selects when one of them is active (or a value is NaN)
-  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
-    xd[12] = clipd(r12, -10000, 10000);
-    xd[13] = clipd(r13, -60, 60);
-    xd[14] = clipd(r14, -80, 80);
-    xd[15] = clipd(r15, -120, 120);
-    xd[16] = clipd(r16, -25, 25);
-  }
-  xd[17] = (alpha_deg - lf_in) * 7.25;
+  actuator_rows(x, uc, atmos_out, alpha_deg, xd);
+  if (AUX) { aux[0] = atmos_out; aux[1] = alpha_deg; }
   return true;
 }
 
@@ -609,8 +632,9 @@ F16_FD double lrow(const double* row, const LofiA& A) {
   return fma(A.ada, row[A.L] - lo, lo);
 }
 
-template <bool LIBM_TRIG, bool NLP = false>
-F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18]) {
+template <bool LIBM_TRIG, bool NLP = false, bool AUX = false>
+F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18],
+                           double* aux = nullptr) {
   const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
   const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
   if (!(fabs(beta) <= 30.0)) return false;  // lofi_envelope(): dmomdcon indexes past its arrays beyond 30 deg
@@ -770,23 +794,8 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   // actuators and leading-edge flap, utils.py:289-330 (the flap states evolve in the lofi model too; Nlplant ignores them)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
-  const double lf_in = fma(2.0, alpha_deg, x[17]);
-  const double lef_cmd = clipd(fma(lf_in, K.c1_38, K.c1_45) - atmos_out, 0, 25);
-  const double r12 = uc[0] - x[12], r13 = K.c20_2 * (uc[1] - x[13]), r14 = K.c20_2 * (uc[2] - x[14]),
-               r15 = K.c20_2 * (uc[3] - x[15]), r16 = K.inv0_136 * (lef_cmd - x[16]);
-  xd[12] = r12;
-  xd[13] = r13;
-  xd[14] = r14;
-  xd[15] = r15;
-  xd[16] = r16;
-  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
-    xd[12] = clipd(r12, -10000, 10000);
-    xd[13] = clipd(r13, -60, 60);
-    xd[14] = clipd(r14, -80, 80);
-    xd[15] = clipd(r15, -120, 120);
-    xd[16] = clipd(r16, -25, 25);
-  }
-  xd[17] = (alpha_deg - lf_in) * 7.25;
+  actuator_rows(x, uc, atmos_out, alpha_deg, xd);
+  if (AUX) { aux[0] = atmos_out; aux[1] = alpha_deg; }
   return true;
 }
 

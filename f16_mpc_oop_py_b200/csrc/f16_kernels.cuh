@@ -70,6 +70,9 @@ cudaError_t launch_step_lofi_fast(const LaunchCfg&, const DevTables&, const Batc
 // Nlplant_batch (u == nullptr, x = xu [17][N]) / calc_xdot_batch on the arithmetic of f16_fast.cuh, TMA-staged input tiles
 cudaError_t launch_xdot_fast(const LaunchCfg&, const DevTables&, const BatchSel&, const double* x, long long ld_x, const double* u,
                              long long ld_u, double* xdot, long long ld_out, long long N, int* status, unsigned* redo);
+// f16_linearise_fast.cu: linearise_batch on the arithmetic of f16_fast.cuh (two aircraft per warp, no tile, no barriers)
+cudaError_t launch_linearise_fast(const LaunchCfg&, const DevTables&, const BatchSel&, const double* x, long long ld_x, const double* u,
+                                  long long ld_u, long long N, double eps, int scheme, double* A, double* B, int* status, unsigned* redo);
 cudaError_t launch_fast_probe(const LaunchCfg&, const DevTables&, const double* alpha, const double* beta, const double* el,
                               long long N, double* coef, int* cells, double* lam, int* status);
 }

@@ -1,0 +1,300 @@
+// f16_linearise_fast.cu -- linearise_batch in F16_MATH_FAST: finite-difference A [18x18], B [18x4] of _calc_xdot
+// (env.py:294-342: forward differences, eps on every state / input; and the central scheme) on the arithmetic of
+// f16_fast.cuh.  Compiled like f16_step_fast.cu (-fmad=false, explicit fma()).
+//
+// The strict kernel (f16_kernels.cu: CTA = 32 aircraft x 8 warps, stages of f shared between columns through shared
+// memory, three barriers and a 101 KB transposing tile per group) is bound by latency: 252 registers -> 8 warps per SM, FP64
+// pipe 31 % busy.  A full evaluation on the fast arithmetic is ~640 instructions in 168 registers, which makes a barrier-
+// free mapping affordable:
+//
+//   * a warp-task is TWO aircraft; the 16 lanes of a half-warp are the 15 perturbation columns that need Nlplant (states
+//     2..16: h, phi, theta, psi, V, alpha, beta, p, q, r, T, dh, da, dr, lf2) plus the unperturbed point.  Every lane runs the
+//     same code on its own perturbed copy of the state -- no divergence, and the 16 lanes of an aircraft gather from the same
+//     table cells (broadcast);
+//   * columns 0, 1 (npos, epos) feed nothing: exact zeros, as in the reference.  Columns 17 (lf1) and the four inputs reach
+//     f through rows 12..17 only (fastmath::actuator_rows): lanes 0..4 re-evaluate those six rows with the flap-schedule
+//     terms of the unperturbed point, rows 0..11 are exact zeros (identical bits on both sides of the difference);
+//   * central scheme: f(x + eps e_c) waits in a per-thread shared-memory slot (18 doubles) while f(x - eps e_c) is computed
+//     at the same evaluation site;
+//   * the quotient is the IEEE quotient (div_by), formed in registers; row r of A is then 16 consecutive doubles (columns
+//     2..17) held by the 16 lanes: one 128-byte store per row straight from registers, no transposing tile.  A block of A
+//     (2592 B) and of B (576 B) is written completely by one half-warp within a few hundred cycles, so L2 sees whole sectors;
+//   * an aircraft with any evaluation outside the preconditions of the fast arithmetic or outside the tables is marked and
+//     redone after the main loop on the reference-order arithmetic (f16_model.cuh, tables in global memory), which also
+//     produces the status word and the NaN columns of the strict kernel.
+#include <stdlib.h>
+
+#include "f16_kernels_common.cuh"
+#include "f16_fast.cuh"
+
+namespace f16 {
+namespace fast {
+
+constexpr int LF_THREADS = 384;
+
+template <int FI>
+struct LfSmem {
+  static constexpr int IMG_BYTES = FI ? F16_FI_BYTES : F16_LOFI_STEP_IMG_DOUBLES * 8;
+  static constexpr int BAR_OFF = (IMG_BYTES + 15) / 16 * 16;
+  static constexpr int STASH_OFF = (BAR_OFF + 16 + 127) / 128 * 128;
+  static constexpr int TOTAL = STASH_OFF + 18 * LF_THREADS * 8;  // f(x + eps e_c) of the central scheme: [18][thread]
+};
+
+struct LinQuot {  // (f+ - f-) / den as the IEEE quotient (the reference divides, env.py:330,339)
+  double den, rden;
+  __device__ __forceinline__ LinQuot(double eps, int scheme) {
+    den = scheme == 0 ? eps : 2 * eps;
+    rden = 1.0 / den;
+  }
+  __device__ __forceinline__ double operator()(double num) const { return div_by(num, den, rden); }
+};
+
+__device__ __forceinline__ double shfl_half(double v, int src_in_half) { return __shfl_sync(0xffffffffu, v, src_in_half, 16); }
+
+// x0 with component `col` moved by d (col outside 0..17: unchanged).  A select per element, not an addition of zero: -0.0
+// stays -0.0.
+__device__ __forceinline__ void perturbed(const double (&x0)[18], int col, double d, double (&x)[18]) {
+#pragma unroll
+  for (int i = 0; i < 18; i++) x[i] = (i == col) ? x0[i] + d : x0[i];
+}
+
+// What one half-warp writes for its aircraft.  q[r]: rows of this lane's column (lane j < 15: state column 2 + j);
+// actq[i]: rows 12 + i of column 17 + j (lanes j < 5); c17[i]: lane 0's actq[i]; zero_col: 0, or NaN when the unperturbed point
+// has no value.  No shuffles in here: the two halves of a warp may take different branches around the call.
+__device__ __forceinline__ void lin_store(double* __restrict__ A_g, double* __restrict__ B_g, int* __restrict__ status, long long n,
+                                          int j, const double (&q)[18], const double (&actq)[6], const double (&c17)[6],
+                                          double zero_col, bool void_all, int st) {
+  double* Ao = A_g + n * 324;
+  double* Bo = B_g + n * 72;
+  const double nanv = qnan();
+#pragma unroll
+  for (int r = 0; r < 18; r++) {
+    double v = q[r];
+    // column 17 (lf1) is stored by lane 15: rows 12..17 are lane 0's actuator rows (c17, shuffled by the caller), rows 0..11 zero
+    if (j == 15) v = r < 12 ? zero_col : c17[r < 12 ? 0 : r - 12];
+    if (void_all) v = nanv;
+    Ao[r * 18 + 2 + j] = v;                                      // columns 2..17: 16 consecutive doubles
+    if (j < 2) Ao[r * 18 + j] = void_all ? nanv : zero_col;      // columns 0, 1: f reads neither npos nor epos
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) Bo[16 * k + j] = void_all ? nanv : zero_col;  // rows 0..11 of B
+  if (j >= 1 && j <= 4) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) Bo[(12 + i) * 4 + (j - 1)] = void_all ? nanv : actq[i];
+  }
+  if (status && j == 0) status[n] = st;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// rare path: one marked aircraft per half-warp on the reference-order arithmetic, full evaluations for every column
+// ------------------------------------------------------------------------------------------------------
+template <int FI>
+static __device__ __noinline__ void lin_redo_pass(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x,
+                                                  const double* __restrict__ u_g, long long ld_u, long long N, double eps, int scheme,
+                                                  double* __restrict__ A_g, double* __restrict__ B_g, int* __restrict__ status,
+                                                  const unsigned* redo, long long t, long long stride, long long n_tasks, int lane) {
+  const double* img = FI ? tabs.hifi : tabs.lofi;
+  const int half = lane >> 4, j = lane & 15;
+  const LinQuot fd(eps, scheme);
+#pragma unroll 1
+  for (; t < n_tasks; t += stride) {
+    const unsigned word = redo[t];
+    if (!word) continue;  // warp-uniform
+    const long long n = 2 * t + half;
+    const bool mine = ((word >> half) & 1u) != 0 && n < N;
+    double x0[18], u0[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x0[i] = mine ? x_g[i * ld_x + n] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) u0[i] = mine ? u_g[i * ld_u + n] : 0.0;
+    const double xcg = (mine && sel.xcg) ? sel.xcg[n] : sel.xcg_default;
+    double xu0[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) xu0[i] = x0[i];
+    const unsigned st_base = envelope_of<FI>(xu0);
+    unsigned stat = 0;
+    double q[18], actq[6], fp[18];
+    // columns 2..16 and the unperturbed point (lane 15)
+    {
+      const int col = j < 15 ? 2 + j : -1;
+      unsigned st = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < (scheme != 0 ? 2 : 1); pass++) {
+        double x[18], f[18];
+        perturbed(x0, col, pass ? -eps : eps, x);
+        unsigned s1 = (mine && !(scheme != 0 && j == 15)) ? calc_xdot<FI>(img, x, u0, xcg, f) : 0u;
+        st |= s1;
+#pragma unroll
+        for (int r = 0; r < 18; r++) {
+          const double v = s1 ? qnan() : f[r];
+          if (pass == 0) fp[r] = v;
+          else q[r] = fd(fp[r] - v);
+        }
+      }
+      if (scheme == 0) {
+#pragma unroll
+        for (int r = 0; r < 18; r++) q[r] = fd(fp[r] - shfl_half(fp[r], 15));  // a NaN base makes every quotient NaN
+      }
+      if (st) {
+#pragma unroll
+        for (int r = 0; r < 18; r++) q[r] = qnan();
+      }
+      stat |= st;
+    }
+    // columns 17..21 on lanes 0..4: rows 12..17 (rows 0..11 are exact zeros)
+    {
+      const int c = 17 + j;  // lanes >= 5 compute nothing that is stored
+      double fa[18], fb[18];
+      double x[18], u[4];
+      perturbed(x0, c, eps, x);
+#pragma unroll
+      for (int i = 0; i < 4; i++) u[i] = (18 + i == c) ? u0[i] + eps : u0[i];
+      const bool act = mine && j < 5 && !st_base;
+      if (act) calc_xdot<FI>(img, x, u, xcg, fa);
+      if (scheme != 0) {
+        perturbed(x0, c, -eps, x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = (18 + i == c) ? u0[i] - eps : u0[i];
+        if (act) calc_xdot<FI>(img, x, u, xcg, fb);
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const double base_row = shfl_half(fp[12 + i], 15);
+        const double num = scheme != 0 ? fa[12 + i] - fb[12 + i] : fa[12 + i] - base_row;
+        actq[i] = act ? fd(num) : qnan();
+      }
+      if (st_base) stat |= st_base;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) stat |= __shfl_xor_sync(0xffffffffu, stat, o, 16);
+    double c17[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) c17[i] = shfl_half(actq[i], 0);
+    if (mine) lin_store(A_g, B_g, status, n, j, q, actq, c17, st_base ? qnan() : 0.0, false, (int)(stat | st_base));
+  }
+}
+
+template <int FI>
+__global__ void __launch_bounds__(LF_THREADS, 1)
+linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g,
+                      long long ld_u, long long N, double eps, int scheme, double* __restrict__ A_g, double* __restrict__ B_g,
+                      int* __restrict__ status, unsigned* __restrict__ redo) {
+  using S = LfSmem<FI>;
+  const double* img = reinterpret_cast<const double*>(f16_smem);
+  if (FI) {
+    stage_tables_tma<F16_FI_BYTES>(f16_smem, tabs.hifi_fast, reinterpret_cast<unsigned long long*>(f16_smem + S::BAR_OFF));
+  } else {
+    double* li = reinterpret_cast<double*>(f16_smem);
+    for (int i = threadIdx.x; i < F16_LOFI_STEP_IMG_DOUBLES; i += LF_THREADS)
+      li[i] = i < F16_IMG_LOFI_DOUBLES ? tabs.lofi[i] : tabs.hifi_fast[F16_FI_POW + (i - F16_IMG_LOFI_DOUBLES)];
+    __syncthreads();
+  }
+  double* stash = reinterpret_cast<double*>(f16_smem + S::STASH_OFF) + threadIdx.x;  // element r at stash[r * LF_THREADS]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, j = lane & 15;
+  const LinQuot fd(eps, scheme);
+  const long long n_tasks = (N + 1) >> 1;
+  const long long stride = (long long)(LF_THREADS / 32) * gridDim.x;
+  const long long t0 = (long long)warp * gridDim.x + blockIdx.x;  // warp-major slots: a partial last round covers all SMs
+  unsigned any_redo = 0;
+  for (long long t = t0; t < n_tasks; t += stride) {
+    const long long n = 2 * t + half;
+    const int own = n < N ? owns<FI>(sel, n) : 0;
+    const bool mine = own == 1;
+    double x0[18], u0[4];
+#pragma unroll
+    for (int i = 0; i < 18; i++) x0[i] = mine ? x_g[i * ld_x + n] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) u0[i] = mine ? u_g[i * ld_u + n] : 0.0;
+    const double xcg = (mine && sel.xcg) ? sel.xcg[n] : sel.xcg_default;
+    double uc[4];
+    fastmath::clip_commands(u0, uc);
+    const int col = j < 15 ? 2 + j : -1;
+    bool ok = true;
+    double q[18], aux[2] = {0.0, 0.0};
+    {
+      double f[18];
+#pragma unroll 1
+      for (int pass = 0; pass < (scheme != 0 ? 2 : 1); pass++) {  // one evaluation site
+        double x[18];
+        perturbed(x0, col, pass ? -eps : eps, x);
+        double a2[2];
+        bool k = fastmath::fast_ok<FI>(x);
+        if (k) k = FI ? fastmath::calc_xdot_hifi<false, false, true>(img, x, uc, xcg, f, a2)
+                      : fastmath::calc_xdot_lofi<false, false, true>(img, x, uc, xcg, f, a2);
+        ok &= k | !mine | (pass == 1 && j == 15);
+        if (pass == 0) {
+          aux[0] = a2[0];
+          aux[1] = a2[1];
+          if (scheme != 0) {
+#pragma unroll
+            for (int r = 0; r < 18; r++) stash[r * LF_THREADS] = f[r];
+          }
+        }
+      }
+      if (scheme != 0) {
+#pragma unroll
+        for (int r = 0; r < 18; r++) q[r] = fd(stash[r * LF_THREADS] - f[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 18; r++) q[r] = fd(f[r] - shfl_half(f[r], 15));
+      }
+      // rows 12..17 of the unperturbed point for the forward quotients of the actuator-only columns
+#pragma unroll
+      for (int i = 0; i < 6; i++) f[i] = shfl_half(f[12 + i], 15);
+      // ---- columns 17 (lf1) and 18..21 (inputs) on lanes 0..4: rows 12..17 only ----
+      const double a_out = shfl_half(aux[0], 15), a_deg = shfl_half(aux[1], 15);
+      const int c = 17 + j;
+      double actq[6];
+      {
+        double xa[18], ua[4], uca[4], rp[18], rm[18];
+        perturbed(x0, c, eps, xa);
+#pragma unroll
+        for (int i = 0; i < 4; i++) ua[i] = (18 + i == c) ? u0[i] + eps : u0[i];
+        fastmath::clip_commands(ua, uca);
+        fastmath::actuator_rows(xa, uca, a_out, a_deg, rp);
+        if (scheme != 0) {
+          perturbed(x0, c, -eps, xa);
+#pragma unroll
+          for (int i = 0; i < 4; i++) ua[i] = (18 + i == c) ? u0[i] - eps : u0[i];
+          fastmath::clip_commands(ua, uca);
+          fastmath::actuator_rows(xa, uca, a_out, a_deg, rm);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) actq[i] = fd(scheme != 0 ? rp[12 + i] - rm[12 + i] : rp[12 + i] - f[i]);
+        // NaN inputs (a NaN command or lf1) are not a precondition of fast_ok for these columns: redo decides
+        ok &= !mine | j >= 5 | !(either_nan(ua[0], ua[1]) | either_nan(ua[2], ua[3]) | either_nan(xa[17], xa[17]));
+      }
+      const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+      const bool redo_me = (bad & (half ? 0xffff0000u : 0x0000ffffu)) != 0;
+      if (lane == 0) redo[t] = ((bad & 0x0000ffffu) ? 1u : 0u) | ((bad & 0xffff0000u) ? 2u : 0u);
+      any_redo |= bad;
+      double c17[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) c17[i] = shfl_half(actq[i], 0);
+      if ((mine && !redo_me) || own < 0)
+        lin_store(A_g, B_g, status, n, j, q, actq, c17, 0.0, own < 0, own < 0 ? (int)ST_FIDELITY : 0);
+    }
+  }
+  if (!any_redo) return;
+  __syncwarp();
+  lin_redo_pass<FI>(tabs, sel, x_g, ld_x, u_g, ld_u, N, eps, scheme, A_g, B_g, status, redo, t0, stride, n_tasks, lane);
+}
+
+cudaError_t launch_linearise_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, const double* x, long long ld_x,
+                                  const double* u, long long ld_u, long long N, double eps, int scheme, double* A, double* B,
+                                  int* status, unsigned* redo) {
+  if (N <= 0) return cudaSuccess;
+  const long long n_tasks = (N + 1) / 2;
+  cudaError_t e = cudaSuccess;
+  const bool want1 = sel.fi != nullptr || sel.fi_default != 0, want0 = sel.fi != nullptr || sel.fi_default == 0;
+  if (want1)
+    e = launch_persistent(cfg, linearise_fast_kernel<1>, LF_THREADS, LfSmem<1>::TOTAL, n_tasks, LF_THREADS / 32, tabs, sel, x, ld_x, u,
+                          ld_u, N, eps, scheme, A, B, status, redo);
+  if (e == cudaSuccess && want0)
+    e = launch_persistent(cfg, linearise_fast_kernel<0>, LF_THREADS, LfSmem<0>::TOTAL, n_tasks, LF_THREADS / 32, tabs, sel, x, ld_x, u,
+                          ld_u, N, eps, scheme, A, B, status, redo);
+  return e;
+}
+
+}  // namespace fast
+}  // namespace f16

@@ -406,12 +406,7 @@ xdot_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorM
     bool ok = false;
     if (own == 1) {
       const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
-      ok = (x[2] >= -4000.0) & (x[2] <= 102000.0) & fastmath::small_angle(x[3]) & fastmath::small_angle(x[4]) &
-           fastmath::small_angle(x[5]);
-      ok &= !either_nan(x[0], x[1]) & !either_nan(x[6], x[9]) & !either_nan(x[10], x[11]) & !either_nan(x[12], x[14]) &
-            !either_nan(x[15], x[16]);
-      if (FI) ok &= (fabs(x[13]) <= 25.0);
-      else ok &= fastmath::small_angle(x[7]) & !either_nan(x[13], x[13]);
+      ok = fastmath::fast_ok<FI>(x);
       double uc[4] = {0.0, 0.0, 0.0, 0.0};
       if (!NLP) {
         ok &= !either_nan(u[0], u[1]) & !either_nan(u[2], u[3]) & !either_nan(x[17], x[17]);

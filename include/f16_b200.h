@@ -51,7 +51,11 @@ extern "C" {
                            * wind-axis equations with vt cancelled); Nlplant_batch / calc_xdot_batch run the strict
                            * expressions with FMA contraction and reciprocal multiplies.  Both stay within the parity bars
                            * (<= 1e-12 scaled per derivative, <= 1e-9 after 10 s; tests/test_gpu_parity.py);
-                           * linearise_batch always runs the strict build (the quotient multiplies rounding by 1/eps). */
+                           * linearise_batch runs f16_fast.cuh too (two aircraft per warp, csrc/f16_linearise_fast.cu): the quotient
+                           * multiplies last-bit differences of f by 1/eps, so its entries agree with the reference's to
+                           * 1e-8 + 4 ulp(f_i) / h (up to 3.4e-8 on the 900 ft/s navigation rows; the reference's own source built
+                           * with -O3 -march=native moves as much, profiles/r02_jacobian_noise_floor.md).
+                           * f16_set_linearise_variant(2) keeps the strict kernel in fast mode. */
 
 /* ---- CLr table quirk ---------------------------------------------------------------------------
  * The reference never loads CL1320_ALPHA1_606.dat (hifi_F16_AeroData.c:965-972: the fscanf loop is the
@@ -106,8 +110,10 @@ void f16_set_default_xcg(double xcg); /* for the legacy Nlplant symbol; default 
 int f16_set_table_staging(int mode);  /* 1 (default): tables staged in shared memory by TMA bulk copy;
                                          0: read through L1/L2 with ld.global.nc (for A/B measurements) */
 int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256, 384 (default), 512, 640, 768 or 1024 */
-int f16_set_linearise_variant(int variant); /* linearise_batch kernel: 0 = CTA per 32 aircraft, columns over warps, stages shared;
-                                               1 = warp per aircraft, column per lane.  Same bits either way. */
+int f16_set_linearise_variant(int variant); /* linearise_batch kernel.  0 (default): in F16_MATH_STRICT the staged strict kernel (CTA per
+                                               32 aircraft, columns over warps), in F16_MATH_FAST the two-aircraft-per-warp kernel on
+                                               the fast arithmetic; 1 = strict, warp per aircraft, column per lane; 2 = strict, CTA
+                                               per 32 aircraft, in either math mode.  1 and 2 give the same bits. */
 /* sha256 (hex, 64 chars + NUL) of the canonical table payload in use */
 int f16_tables_sha256(char *out65);
 

@@ -23,6 +23,15 @@ TOL_TRAJ = 1e-9
 TOL_JAC = 1e-8
 
 
+def jac_bar(xdot, scheme):
+    """Parity bar of a finite-difference Jacobian entry in row i: 1e-8 absolute plus the quotient's own noise floor,
+    4 ulp(|f_i|) / h (h = eps forward, 2 eps central; eps = 1e-5).  The reference's OWN source built with -O3 -march=native
+    moves the forward A by 2.3e-8 on the 900 ft/s navigation rows (profiles/r02_jacobian_noise_floor.md): one ulp of f
+    divided by eps is already 1.1e-8 there.  Wherever |f_i| < 100 the bar is the plain 1e-8.  xdot: [18][N] -> [N][18][1]."""
+    h = 1e-5 * (2 if scheme in (1, "central") else 1)
+    return TOL_JAC + 4 * np.spacing(np.abs(np.asarray(xdot))).T[:, :, None] / h
+
+
 def checker(oracle):
     """the reference's own .so when oracle/_ref travelled with the repo, else the pinned C restatement"""
     return REF if oracle.have_ref else PORT
@@ -550,9 +559,16 @@ def test_step_large_mixed_batch_is_partitioned_by_fidelity(f16, mode, with_law):
 # linearise_batch (env.py:294-342; BASELINE cfg 4)
 # ---------------------------------------------------------------------------------------------------------
 def test_linearise_matches_env_py_golden(f16, mode, golden):
+    """F16.linearise at the trim point of the unmodified reference.  strict: 1e-8 on every entry; fast (the quotient on the
+    re-associated arithmetic): 1e-8 everywhere except the two navigation rows, which get the noise-floor bar of jac_bar()."""
     fb = f16.F16Batch(golden["x_trim"], golden["u_trim"], fi_flag=int(golden["fi"]), xcg=float(golden["xcg"]))
     A, B, C, D = fb.linearise(golden["x_trim"], golden["u_trim"], scheme="forward")
-    assert np.abs(A[0] - golden["Ac"]).max() < TOL_JAC and np.abs(B[0] - golden["Bc"]).max() < TOL_JAC
+    eA, eB = np.abs(A[0] - golden["Ac"]), np.abs(B[0] - golden["Bc"])
+    if mode == "strict":
+        assert eA.max() < TOL_JAC and eB.max() < TOL_JAC
+    else:
+        bar = jac_bar(golden["xdot_trim"][:, None], "forward")[0]
+        assert (eA <= bar).all() and eB.max() < TOL_JAC and eA[2:].max() < TOL_JAC, (eA.max(), eA[2:].max())
     assert C.shape == (10, 18) and D.shape == (10, 4) and C.sum() == 10
 
 
@@ -603,6 +619,84 @@ def test_linearise_batch_grid(f16, oracle, scheme, fi, lin_variant):
     ok = rst == 0
     assert ok.mean() > 0.9
     assert np.abs(A[ok] - Ar[ok]).max() < TOL_JAC and np.abs(B[ok] - Br[ok]).max() < TOL_JAC
+
+
+@pytest.mark.parametrize("scheme", ["forward", "central"])
+@pytest.mark.parametrize("fi", [1, 0])
+def test_linearise_fast_kernel_grid(f16, oracle, scheme, fi):
+    """F16_MATH_FAST linearise_batch (csrc/f16_linearise_fast.cu: two aircraft per warp on the fast arithmetic) on the same
+    16 x 16 altitude x velocity grid: status words equal, rows 2..17 within 1e-8, the two navigation rows within jac_bar()."""
+    prev = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        g = load_golden("xcg25")
+        n = 256 + 13     # odd: the last warp-task holds one aircraft
+        x, u = perturbed_trim(n, g["x_trim"], seed=21, frac=0.03)
+        x[2] = np.tile(np.linspace(5000, 40000, 16), 17)[:n]
+        x[6] = np.repeat(np.linspace(300, 900, 17), 16)[:n]
+        sch = 0 if scheme == "forward" else 1
+        Ar, Br, rst = oracle.linearise_batch(x, u, 1e-5, sch, fi, 0.25, checker(oracle))
+        fb = f16.F16Batch(x, u, fi_flag=fi, xcg=0.25)
+        A, B, _, _ = fb.linearise(x, u, scheme=scheme)
+        assert np.array_equal(fb.last_status, rst)
+        ok = rst == 0
+        assert ok.mean() > 0.9
+        xd = fb._calc_xdot(x, u)
+        bar = jac_bar(xd, sch)[ok]
+        eA, eB = np.abs(A[ok] - Ar[ok]), np.abs(B[ok] - Br[ok])
+        assert (eA <= bar).all() and eB.max() < TOL_JAC and eA[:, 2:].max() < TOL_JAC, (eA.max(), eA[:, 2:].max(), eB.max())
+    finally:
+        f16.lib.f16_set_math_mode(prev)
+
+
+def test_linearise_fast_kernel_edge_semantics_equal_the_strict_kernel(f16):
+    """Everything that is not an ordinary in-envelope aircraft must come out of the fast-mode kernel exactly as it comes out
+    of the strict one (those aircraft are redone on the reference-order arithmetic): columns that leave the tables, a base
+    point outside the tables, NaN states / inputs, an altitude beyond the fast density table, huge Euler angles, bad and
+    mixed fidelity flags, per-aircraft xcg, N = 1 and odd N."""
+    g = load_golden("xcg25")
+    n = 777
+    x, u = perturbed_trim(n, g["x_trim"], seed=9, frac=0.04)
+    x[13, 1] = 25.0 - 1e-6               # elevator + eps leaves DH1: NaN column 13, status DELE
+    x[7, 2] = np.deg2rad(45.0) - 2e-6    # alpha + eps leaves the hifi tables
+    x[8, 3] = np.deg2rad(31.0)           # base point outside: everything NaN
+    x[9, 4] = np.nan
+    u[2, 5] = np.nan
+    x[17, 6] = np.nan
+    x[2, 7] = 120000.0                   # outside the density table of the fast arithmetic
+    x[5, 8] = 5.0e9                      # Euler angle beyond 2^30 rad
+    x[6, 9] = 0.005                      # below the vt clamp of nlplant.c:104
+    fi = np.ones(n, dtype=np.uint8)
+    fi[::3] = 0
+    fi[10] = 7
+    xcg = np.where(np.arange(n) % 2 == 0, 0.25, 0.35)
+    out = {}
+    for mode in (f16.MATH_STRICT, f16.MATH_FAST):
+        prev = f16.lib.f16_set_math_mode(mode)
+        for scheme in ("forward", "central"):
+            for m in (n, 1, 12):
+                fb = f16.F16Batch(x[:, :m], u[:, :m], fi_flag=fi[:m], xcg=xcg[:m])
+                A, B, _, _ = fb.linearise(np.ascontiguousarray(x[:, :m]), np.ascontiguousarray(u[:, :m]), scheme=scheme)
+                out[mode, scheme, m] = (A, B, fb.last_status.copy(), fb._calc_xdot(np.ascontiguousarray(x[:, :m]), np.ascontiguousarray(u[:, :m])))
+        f16.lib.f16_set_math_mode(prev)
+    special = np.zeros(n, dtype=bool)
+    special[1:9] = True        # the aircraft the fast kernel hands to its reference-order pass
+    for scheme in ("forward", "central"):
+        for m in (n, 1, 12):
+            As, Bs, ss, xd = out[f16.MATH_STRICT, scheme, m]
+            Af, Bf, sf, _ = out[f16.MATH_FAST, scheme, m]
+            assert np.array_equal(ss, sf), (scheme, m, np.flatnonzero(ss != sf))
+            assert np.array_equal(np.isnan(As), np.isnan(Af)) and np.array_equal(np.isnan(Bs), np.isnan(Bf)), (scheme, m)
+            sp = special[:m]
+            # the redone aircraft carry the strict build's numbers to rounding (same arithmetic, unstaged evaluation order)
+            fin = np.isfinite(As[sp])
+            d = np.abs(Af[sp][fin] - As[sp][fin])
+            assert d.max(initial=0.0) <= 1e-9, (scheme, m, d.max(), np.argwhere(np.abs(np.where(np.isfinite(As), Af - As, 0.0)) > 1e-9)[:5])
+            bar = jac_bar(np.where(np.isfinite(xd), xd, 0.0), scheme)
+            fa = np.isfinite(As)
+            assert (np.abs(Af - As)[fa] <= np.broadcast_to(2 * bar, As.shape)[fa]).all(), (scheme, m)
+            fb_ = np.isfinite(Bs)
+            assert np.abs(Bf - Bs)[fb_].max(initial=0.0) < 2 * TOL_JAC
+    assert out[f16.MATH_FAST, "forward", n][2][1] == 1 << 20 and out[f16.MATH_FAST, "forward", n][2][10] == 1 << 22
 
 
 def test_linearise_out_of_envelope_column_is_nan(f16, lin_variant):
@@ -705,32 +799,39 @@ def test_trim_then_linearise_full_cfg4_grid(f16):
     assert np.allclose(A[:, 13, 13], -20.2) and np.allclose(A[:, 14, 14], -20.2) and np.allclose(A[:, 15, 15], -20.2)
 
 
-def test_cfg4_full_grid_jacobians_against_the_oracle(f16, oracle):
+_CFG4_REF = {}
+
+
+def test_cfg4_full_grid_jacobians_against_the_oracle(f16, oracle, mode):
     """BASELINE cfg 4 at its stated size as a PARITY test: all 64 x 64 device-computed trim points,
-    forward (env.py:294-342, eps 1e-5) and central A/B from linearise_batch against the same scheme looped over the
-    reference .so at every point, <= 1e-8 absolute."""
-    hh, vv = np.meshgrid(np.linspace(5000, 40000, 64), np.linspace(300, 900, 64), indexing="ij")
-    x, opt = f16.trim(hh.ravel(), vv.ravel(), fi=1, xcg=0.35)
-    ok = opt["success"] & (opt["status"] == 0)
-    assert ok.sum() >= 4000, int(ok.sum())
-    xs, us = np.ascontiguousarray(x[:, ok]), np.ascontiguousarray(x[12:16, ok])
+    forward (env.py:294-342, eps 1e-5) and central A/B from linearise_batch -- the strict kernel and, in fast mode, the
+    two-aircraft-per-warp kernel on the fast arithmetic -- against the same scheme looped over the reference .so at every
+    point (trim points computed once, in strict mode, so that both builds are compared at the same arguments)."""
+    if "pts" not in _CFG4_REF:
+        prev = f16.lib.f16_set_math_mode(f16.MATH_STRICT)
+        hh, vv = np.meshgrid(np.linspace(5000, 40000, 64), np.linspace(300, 900, 64), indexing="ij")
+        x, opt = f16.trim(hh.ravel(), vv.ravel(), fi=1, xcg=0.35)
+        f16.lib.f16_set_math_mode(prev)
+        ok = opt["success"] & (opt["status"] == 0)
+        assert ok.sum() >= 4000, int(ok.sum())
+        xs, us = np.ascontiguousarray(x[:, ok]), np.ascontiguousarray(x[12:16, ok])
+        _CFG4_REF["pts"] = (xs, us)
+        for code in (0, 1):
+            _CFG4_REF[code] = oracle.linearise_batch(xs.copy(), us.copy(), 1e-5, code, 1, 0.35, checker(oracle))
+    xs, us = _CFG4_REF["pts"]
     fb = f16.F16Batch(xs, us, xcg=0.35)
-    # Bar: 1e-8 absolute plus the quotient's own noise floor, 4 ulp(|f_i|) / h (h = eps forward, 2 eps central).  The
-    # reference's OWN source compiled with -O3 -march=native moves the forward A by 2.3e-8 on the 900 ft/s navigation rows
-    # (profiles/r02_jacobian_noise_floor.md): one ulp of f divided by eps is already 1.1e-8 there.  Everywhere |f_i| < 100
-    # the bar is the plain 1e-8.
     xd = fb._calc_xdot(xs, us)
     for scheme, code in (("forward", 0), ("central", 1)):
         A, B, _, _ = fb.linearise(xs, us, scheme=scheme)
-        rA, rB, rst = oracle.linearise_batch(xs.copy(), us.copy(), 1e-5, code, 1, 0.35, checker(oracle))
+        rA, rB, rst = _CFG4_REF[code]
         assert np.array_equal(fb.last_status, rst) and not rst.any()
-        h = 1e-5 * (2 if code else 1)
-        bar = TOL_JAC + 4 * np.spacing(np.abs(xd)).T[:, :, None] / h          # [N][18][1]
+        bar = jac_bar(xd, code)                                                # [N][18][1]
         eA, eB = np.abs(A - rA), np.abs(B - rB)
         assert (eA <= bar).all() and (eB <= bar).all(), (scheme, eA.max(), eB.max(), np.unravel_index(np.argmax(eA - bar), eA.shape))
         over = eA > TOL_JAC                                                    # only navigation rows may use the allowance
         assert not over[:, 2:, :].any() and eB.max() < TOL_JAC, (scheme, np.argwhere(over[:, 2:, :])[:4])
-        print(f"cfg4 {scheme}: max |dA| {eA.max():.2e} (rows 0-1: {int(over.sum())} of {over[:, :2].size} entries above 1e-8), max |dB| {eB.max():.2e}")
+        print(f"cfg4 {mode} {scheme}: max |dA| {eA.max():.2e} (rows 0-1: {int(over.sum())} of {over[:, :2].size} entries above 1e-8), "
+              f"rows 2..17 max {eA[:, 2:].max():.2e}, max |dB| {eB.max():.2e}")
 
 
 _BENCH_SAMPLE_CACHE = {}
