@@ -31,24 +31,32 @@ namespace f16 {
 namespace fast {
 
 constexpr int LF_THREADS = 384;
+constexpr int LF_IN_LD = 24;  // 18 states + 4 inputs (+ 2 pad) per staged aircraft
 
 template <int FI>
 struct LfSmem {
   static constexpr int IMG_BYTES = FI ? F16_FI_BYTES : F16_LOFI_STEP_IMG_DOUBLES * 8;
   static constexpr int BAR_OFF = (IMG_BYTES + 15) / 16 * 16;
   static constexpr int STASH_OFF = (BAR_OFF + 16 + 127) / 128 * 128;
-  static constexpr int TOTAL = STASH_OFF + 18 * LF_THREADS * 8;  // f(x + eps e_c) of the central scheme: [18][thread]
+  static constexpr int IN_OFF = STASH_OFF + 18 * LF_THREADS * 8;  // stash: f(x + eps e_c) of the central scheme, [18][thread]
+  static constexpr int TOTAL = IN_OFF + (LF_THREADS / 32) * 2 * 2 * LF_IN_LD * 8;  // per warp: 2 stages x 2 aircraft x 24 doubles
 };
 
-struct LinQuot {  // (f+ - f-) / den as the IEEE quotient (the reference divides, env.py:330,339)
+// (f+ - f-) / den (the reference divides, env.py:330,339).  The reference-order pass forms the IEEE quotient (div_by); the fast
+// pass multiplies by the rounded reciprocal: one ulp of the quotient, against a numerator that carries 1e5 ulp of f.
+struct LinQuot {
   double den, rden;
   __device__ __forceinline__ LinQuot(double eps, int scheme) {
     den = scheme == 0 ? eps : 2 * eps;
     rden = 1.0 / den;
   }
   __device__ __forceinline__ double operator()(double num) const { return div_by(num, den, rden); }
+  __device__ __forceinline__ double fast(double num) const { return num * rden; }
 };
 
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ double shfl_half(double v, int src_in_half) { return __shfl_sync(0xffffffffu, v, src_in_half, 16); }
 
 // x0 with component `col` moved by d (col outside 0..17: unchanged).  A select per element, not an addition of zero: -0.0
@@ -191,32 +199,55 @@ linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
   }
   double* stash = reinterpret_cast<double*>(f16_smem + S::STASH_OFF) + threadIdx.x;  // element r at stash[r * LF_THREADS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, j = lane & 15;
+  // input staging: the 22 doubles of each of a task's two aircraft, two stages per warp, filled by cp.async one task ahead
+  double* inbuf = reinterpret_cast<double*>(f16_smem + S::IN_OFF) + warp * (2 * 2 * LF_IN_LD);
   const LinQuot fd(eps, scheme);
   const long long n_tasks = (N + 1) >> 1;
   const long long stride = (long long)(LF_THREADS / 32) * gridDim.x;
   const long long t0 = (long long)warp * gridDim.x + blockIdx.x;  // warp-major slots: a partial last round covers all SMs
+  const double* src = lane < 18 ? x_g + lane * ld_x : u_g + (lane < 22 ? lane - 18 : 0) * ld_u;  // the plane this lane fetches
+  auto prefetch = [&](long long task, int stage) {
+    if (task < n_tasks && lane < 22) {
+      const long long na = 2 * task;
+      double* dst = inbuf + stage * (2 * LF_IN_LD) + lane;
+      cp_async8(dst, src + na);
+      if (na + 1 < N) cp_async8(dst + LF_IN_LD, src + na + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(t0, 0);
   unsigned any_redo = 0;
-  for (long long t = t0; t < n_tasks; t += stride) {
+  int stage = 0;
+  const int col = j < 15 ? 2 + j : -1;
+  for (long long t = t0; t < n_tasks; t += stride, stage ^= 1) {
     const long long n = 2 * t + half;
     const int own = n < N ? owns<FI>(sel, n) : 0;
     const bool mine = own == 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     double x0[18], u0[4];
+    {
+      const double* row = inbuf + stage * (2 * LF_IN_LD) + half * LF_IN_LD;
 #pragma unroll
-    for (int i = 0; i < 18; i++) x0[i] = mine ? x_g[i * ld_x + n] : 0.0;
+      for (int i = 0; i < 18; i++) x0[i] = row[i];   // a half without an aircraft of this launch computes on whatever the slot
 #pragma unroll
-    for (int i = 0; i < 4; i++) u0[i] = mine ? u_g[i * ld_u + n] : 0.0;
+      for (int i = 0; i < 4; i++) u0[i] = row[18 + i];  // holds: nothing of it is stored, and `ok` ignores it
+    }
+    prefetch(t + stride, stage ^ 1);
     const double xcg = (mine && sel.xcg) ? sel.xcg[n] : sel.xcg_default;
     double uc[4];
     fastmath::clip_commands(u0, uc);
-    const int col = j < 15 ? 2 + j : -1;
     bool ok = true;
     double q[18], aux[2] = {0.0, 0.0};
     {
       double f[18];
 #pragma unroll 1
       for (int pass = 0; pass < (scheme != 0 ? 2 : 1); pass++) {  // one evaluation site
+        const double d = pass ? -eps : eps;
         double x[18];
-        perturbed(x0, col, pass ? -eps : eps, x);
+        x[0] = x0[0]; x[1] = x0[1]; x[17] = x0[17];
+#pragma unroll
+        for (int i = 2; i < 17; i++) x[i] = (i == col) ? x0[i] + d : x0[i];  // a select, not "+ 0": -0.0 stays -0.0
         double a2[2];
         bool k = fastmath::fast_ok<FI>(x);
         if (k) k = FI ? fastmath::calc_xdot_hifi<false, false, true>(img, x, uc, xcg, f, a2)
@@ -233,36 +264,38 @@ linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
       }
       if (scheme != 0) {
 #pragma unroll
-        for (int r = 0; r < 18; r++) q[r] = fd(stash[r * LF_THREADS] - f[r]);
+        for (int r = 0; r < 18; r++) q[r] = fd.fast(stash[r * LF_THREADS] - f[r]);
       } else {
 #pragma unroll
-        for (int r = 0; r < 18; r++) q[r] = fd(f[r] - shfl_half(f[r], 15));
+        for (int r = 0; r < 18; r++) q[r] = fd.fast(f[r] - shfl_half(f[r], 15));
       }
       // rows 12..17 of the unperturbed point for the forward quotients of the actuator-only columns
 #pragma unroll
       for (int i = 0; i < 6; i++) f[i] = shfl_half(f[12 + i], 15);
       // ---- columns 17 (lf1) and 18..21 (inputs) on lanes 0..4: rows 12..17 only ----
       const double a_out = shfl_half(aux[0], 15), a_deg = shfl_half(aux[1], 15);
-      const int c = 17 + j;
       double actq[6];
       {
+        // only x[12..17] and the commands enter actuator_rows: lane 0 moves lf1, lanes 1..4 one command each
         double xa[18], ua[4], uca[4], rp[18], rm[18];
-        perturbed(x0, c, eps, xa);
 #pragma unroll
-        for (int i = 0; i < 4; i++) ua[i] = (18 + i == c) ? u0[i] + eps : u0[i];
+        for (int i = 0; i < 17; i++) xa[i] = x0[i];
+        xa[17] = j == 0 ? x0[17] + eps : x0[17];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ua[i] = (1 + i == j) ? u0[i] + eps : u0[i];
         fastmath::clip_commands(ua, uca);
         fastmath::actuator_rows(xa, uca, a_out, a_deg, rp);
         if (scheme != 0) {
-          perturbed(x0, c, -eps, xa);
+          xa[17] = j == 0 ? x0[17] - eps : x0[17];
 #pragma unroll
-          for (int i = 0; i < 4; i++) ua[i] = (18 + i == c) ? u0[i] - eps : u0[i];
+          for (int i = 0; i < 4; i++) ua[i] = (1 + i == j) ? u0[i] - eps : u0[i];
           fastmath::clip_commands(ua, uca);
           fastmath::actuator_rows(xa, uca, a_out, a_deg, rm);
         }
 #pragma unroll
-        for (int i = 0; i < 6; i++) actq[i] = fd(scheme != 0 ? rp[12 + i] - rm[12 + i] : rp[12 + i] - f[i]);
-        // NaN inputs (a NaN command or lf1) are not a precondition of fast_ok for these columns: redo decides
-        ok &= !mine | j >= 5 | !(either_nan(ua[0], ua[1]) | either_nan(ua[2], ua[3]) | either_nan(xa[17], xa[17]));
+        for (int i = 0; i < 6; i++) actq[i] = fd.fast(scheme != 0 ? rp[12 + i] - rm[12 + i] : rp[12 + i] - f[i]);
+        // a NaN command or lf1 is not a precondition of fast_ok: the reference-order pass decides what it means
+        ok &= !mine | !(either_nan(u0[0], u0[1]) | either_nan(u0[2], u0[3]) | either_nan(x0[17], x0[17]));
       }
       const unsigned bad = __ballot_sync(0xffffffffu, !ok);
       const bool redo_me = (bad & (half ? 0xffff0000u : 0x0000ffffu)) != 0;
@@ -271,10 +304,31 @@ linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
       double c17[6];
 #pragma unroll
       for (int i = 0; i < 6; i++) c17[i] = shfl_half(actq[i], 0);
-      if ((mine && !redo_me) || own < 0)
-        lin_store(A_g, B_g, status, n, j, q, actq, c17, 0.0, own < 0, own < 0 ? (int)ST_FIDELITY : 0);
+      if (mine && !redo_me) {
+        // lane 15 holds the unperturbed point: its own quotients are exact zeros (identical bits on both sides), which is what
+        // rows 0..11 of column 17 are; rows 12..17 of that column are lane 0's actuator rows
+#pragma unroll
+        for (int i = 0; i < 6; i++) q[12 + i] = j == 15 ? c17[i] : q[12 + i];
+        double* Ao = A_g + n * 324;
+        double* Bo = B_g + n * 72;
+#pragma unroll
+        for (int r = 0; r < 18; r++) {
+          Ao[r * 18 + 2 + j] = q[r];          // columns 2..17: 16 consecutive doubles
+          if (j < 2) Ao[r * 18 + j] = 0.0;    // columns 0, 1: f reads neither npos nor epos
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) Bo[16 * k + j] = 0.0;  // rows 0..11 of B
+        if (j >= 1 && j <= 4) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) Bo[(12 + i) * 4 + (j - 1)] = actq[i];
+        }
+        if (status && j == 0) status[n] = 0;
+      } else if (own < 0) {
+        lin_store(A_g, B_g, status, n, j, q, actq, c17, 0.0, true, (int)ST_FIDELITY);
+      }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (!any_redo) return;
   __syncwarp();
   lin_redo_pass<FI>(tabs, sel, x_g, ld_x, u_g, ld_u, N, eps, scheme, A_g, B_g, status, redo, t0, stride, n_tasks, lane);

@@ -6,7 +6,11 @@ rep, tasks = sys.argv[1], float(sys.argv[2])
 win = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, data = rows[1], rows[2:]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0    # which launch of the report
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+rows = rows[starts[which]:starts[which + 1]]
+print(rows[0][1][:110])
+hdr, data = rows[1], [r for r in rows[2:] if len(r) == len(rows[1])]
 iS, iE, iSt = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
 tot, stall, n, ns = collections.Counter(), collections.Counter(), 0, 0
 def opc(src):
