@@ -317,9 +317,18 @@ def run_ours(args):
     jac = None
     if args.lin_variant is not None:
         L.f16_set_linearise_variant(args.lin_variant)
+    jac_strict = None
     if not args.no_jacobians:
         jac = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 1)
         jac_fwd = measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 0)
+        for j in (jac, jac_fwd):
+            j["kernel"] = ("linearise_fast_kernel (f16_fast.cuh arithmetic, two aircraft per warp)"
+                           if args.math == "fast" and not args.lin_variant else "linearise_kernel (reference operation order, staged)")
+        if args.math == "fast" and not args.lin_variant:   # the strict (parity-build) kernel beside it
+            L.f16_set_linearise_variant(2)
+            jac_strict = {"central": measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 1),
+                          "forward": measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 0)}
+            L.f16_set_linearise_variant(0)
 
     # max over ranks (timings are the slowest rank's); the only collective: end-of-run statistics
     from f16_mpc_oop_py_b200 import shard
@@ -384,6 +393,11 @@ def run_ours(args):
                 j["fp64_frac"] = j["value"] * j["flop_per_jacobian"] / 1e12 / peak_tf if peak_tf else None
                 j["value_all_gpus"] = j["value"] * world
             line["jacobians"] = {"central": jac, "forward": jac_fwd}
+            if jac_strict:
+                for j in jac_strict.values():
+                    j["fp64_frac"] = j["value"] * j["flop_per_jacobian"] / 1e12 / peak_tf if peak_tf else None
+                    j["kernel"] = "linearise_kernel (reference operation order, staged): f16_set_linearise_variant(2)"
+                line["jacobians"]["strict_build"] = jac_strict
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -410,8 +424,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-jacobians", action="store_true", help="skip the linearise_batch (Jacobians/s) measurement")
-    ap.add_argument("--jac-points", type=int, default=1 << 17, help="trim points per GPU in the Jacobian measurement")
-    ap.add_argument("--lin-variant", type=int, default=None, help="linearise kernel: 0 CTA per 32 aircraft, 1 warp per aircraft")
+    ap.add_argument("--jac-points", type=int, default=1 << 20,
+                    help="trim points per GPU in the Jacobian measurement (SURVEY.md 8d: a 2^20-point batch for the throughput figure)")
+    ap.add_argument("--lin-variant", type=int, default=None,
+                    help="linearise kernel: 0 default (fast math: two aircraft per warp on the fast arithmetic), 1 strict warp per "
+                         "aircraft, 2 strict CTA per 32 aircraft")
     ap.add_argument("--ref-aircraft", type=int, default=4096, help="aircraft in the CPU sample")
     ap.add_argument("--ref-euler-steps", type=int, default=200, help="Euler steps in the CPU sample")
     args = ap.parse_args()
