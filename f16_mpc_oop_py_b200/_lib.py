@@ -72,6 +72,7 @@ def _load():
     L.trim_batch_dev.argtypes = [c_vp, c_vp, c_ll, ctypes.c_double, ctypes.c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, ctypes.c_int,
                                  c_vp, ctypes.c_double, c_vp]
     L.f16_set_linearise_variant.argtypes = [ctypes.c_int]
+    L.f16_set_step_chunking.argtypes = [ctypes.c_int]
     L.reduce_jacobian_batch.argtypes = [c_vp, c_ll, c_vp, c_vp]
     L.discretise_batch.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, ctypes.c_double, c_vp, c_vp]
     L.dlqr_batch.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_ll, c_vp, c_vp, c_vp]

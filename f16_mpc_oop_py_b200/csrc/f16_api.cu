@@ -54,13 +54,14 @@ struct State {
   bool smem_tables = true;
   int step_threads = 384;
   int lin_variant = 0;
+  bool step_chunking = true;
   double default_xcg = 0.25;
   int last_status = 0;
   unsigned long long launches = 0;
   // legacy single-aircraft path: mapped pinned host memory, the kernel reads and writes it directly
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
-  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk, b_redo;
+  DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk, b_redo, b_prog;
 };
 
 State G;
@@ -152,6 +153,7 @@ int init_locked(const char* table_path, int device) {
   if (const char* v = getenv("F16_CLR")) G.clr_mode = (!strcmp(v, "file") || !strcmp(v, "1")) ? F16_CLR_FROM_FILE : F16_CLR_AS_BUILT;
   if (const char* v = getenv("F16_STEP_THREADS")) G.step_threads = atoi(v);
   if (const char* v = getenv("F16_TABLE_STAGING")) G.smem_tables = atoi(v) != 0;
+  if (const char* v = getenv("F16_STEP_CHUNKING")) G.step_chunking = atoi(v) != 0;
   if (const char* v = getenv("F16_LIN_VARIANT")) G.lin_variant = (atoi(v) == 1 || atoi(v) == 2) ? atoi(v) : 0;
 
   int rc = upload_tables();
@@ -173,6 +175,9 @@ f16::LaunchCfg cfg(bool smem_tables) {
   c.smem_tables = smem_tables;
   c.lin_variant = G.lin_variant;
   c.launch_counter = &G.launches;
+  c.step_chunking = G.step_chunking;
+  c.step_progress = (int*)G.b_prog.p;
+  c.step_progress_cap = (long long)(G.b_prog.cap / 4);
   return c;
 }
 f16::DevTables tabs() { return f16::DevTables{G.d_hifi, G.d_lofi, G.d_hifi_fast, 0}; }
@@ -250,7 +255,7 @@ void f16_shutdown(void) {
   cudaSetDevice(G.device);
   cudaStreamSynchronize(G.stream);
   for (DevBuf* b : {&G.b_in, &G.b_in2, &G.b_out, &G.b_fi, &G.b_xcg, &G.b_st, &G.b_st2, &G.b_a, &G.b_b, &G.b_flush, &G.b_l1, &G.b_l2,
-                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum, &G.b_perm, &G.b_pscr, &G.b_px, &G.b_pu, &G.b_pxcg, &G.b_pst, &G.b_pk, &G.b_redo})
+                    &G.b_l3, &G.b_l4, &G.b_l5, &G.b_sum, &G.b_perm, &G.b_pscr, &G.b_px, &G.b_pu, &G.b_pxcg, &G.b_pst, &G.b_pk, &G.b_redo, &G.b_prog})
     b->release();
   if (G.d_hifi) cudaFree(G.d_hifi);
   if (G.d_lofi) cudaFree(G.d_lofi);
@@ -303,6 +308,13 @@ int f16_set_step_threads(int threads) {
   std::lock_guard<std::mutex> lk(G_mu);
   int prev = G.step_threads;
   G.step_threads = threads;
+  return prev;
+}
+
+int f16_set_step_chunking(int on) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.step_chunking ? 1 : 0;
+  G.step_chunking = on != 0;
   return prev;
 }
 
@@ -397,6 +409,11 @@ int calc_xdot_batch_dev(const double* x_soa, long long ld_x, const double* u_soa
   return F16_OK;
 }
 
+// scratch of the time-chunked step schedule (one int per 32 aircraft); without it the launch falls back to the plain kernel
+static void reserve_step_progress(long long N) {
+  if (G.step_chunking && N > 0 && G.b_prog.reserve((size_t)((N + 31) / 32) * 4) != cudaSuccess) cudaGetLastError();
+}
+
 // A mixed batch (per-aircraft fidelity flags) for the fused step: ordered by fidelity first, so that each of the two launches
 // runs on a contiguous range with every lane busy (f16_partition.cu).  Applies when the reorder is amortised
 // (N >= 4096 aircraft, K >= 8 steps); *handled = false leaves the call to the per-lane masking of the kernels.
@@ -461,6 +478,7 @@ int step_batch_dev(double* x_soa, long long ld_x, const double* u_soa, long long
   if (lqr && (lqr->n_sel < 0 || lqr->n_sel > 18)) { set_err("step_batch_dev: lqr.n_sel out of range"); return F16_ERR_ARG; }
   if (lqr) for (int j = 0; j < lqr->n_sel; j++) if (lqr->sel[j] < 0 || lqr->sel[j] > 17) { set_err("step_batch_dev: lqr.sel out of range"); return F16_ERR_ARG; }
   // tables go to shared memory whenever the launch does real work; a handful of aircraft-steps read them via L2
+  reserve_step_progress(N);
   bool handled = false;
   if ((rc = step_partitioned(x_soa, ld_x, u_soa, ld_u, N, K, dt, lqr, fi, xcg, xcg_default, status, steps_done, &handled)) != F16_OK)
     return rc;
@@ -557,6 +575,7 @@ int step_batch(double* x_soa, const double* u_soa, long long N, int K, double dt
   if ((rc = stage_sel(fi, xcg, N, &d_fi, &d_xcg)) != F16_OK) return rc;
   H2D(G.b_in.p, x_soa, 18 * n * 8);
   H2D(G.b_in2.p, u_soa, 4 * n * 8);
+  reserve_step_progress(N);
   bool handled = false;
   if ((rc = step_partitioned((double*)G.b_in.p, N, (const double*)G.b_in2.p, N, N, K, dt, lqr, d_fi, d_xcg, xcg_default,
                              (int*)G.b_st.p, (int*)G.b_st2.p, &handled)) != F16_OK)

@@ -28,6 +28,10 @@ struct LaunchCfg {
   bool smem_tables;  // stage tables in shared memory with TMA bulk copies (default) or read them through L1/L2
   int lin_variant;   // linearise kernel: 0 = CTA per 32 aircraft with staged columns, 1 = warp per aircraft
   unsigned long long* launch_counter;
+  // time-chunked scheduling of the fast hifi step (f16_step_fast.cu): on/off, and the device scratch of one int per 32 aircraft
+  bool step_chunking = false;
+  int* step_progress = nullptr;
+  long long step_progress_cap = 0;
 };
 
 #define F16_DECLARE_LAUNCHERS                                                                                        \

@@ -110,6 +110,8 @@ void f16_set_default_xcg(double xcg); /* for the legacy Nlplant symbol; default 
 int f16_set_table_staging(int mode);  /* 1 (default): tables staged in shared memory by TMA bulk copy;
                                          0: read through L1/L2 with ld.global.nc (for A/B measurements) */
 int f16_set_step_threads(int threads); /* CTA size of the fused step kernel: 256, 384 (default), 512, 640, 768 or 1024 */
+int f16_set_step_chunking(int on);     /* 1 (default): long runs of the fast hifi step are scheduled in time chunks (work item = 32 aircraft x
+                                          K/16 steps) so the persistent grid has no tail; 0: one warp-task = all K steps.  Same bits. */
 int f16_set_linearise_variant(int variant); /* linearise_batch kernel.  0 (default): in F16_MATH_STRICT the staged strict kernel (CTA per
                                                32 aircraft, columns over warps), in F16_MATH_FAST the two-aircraft-per-warp kernel on
                                                the fast arithmetic; 1 = strict, warp per aircraft, column per lane; 2 = strict, CTA

@@ -441,6 +441,43 @@ def test_step_table_staging_variants_agree(f16, mode):
         assert np.array_equal(o, outs[0])
 
 
+@pytest.mark.parametrize("with_law", [False, True])
+def test_step_time_chunked_schedule_equals_the_plain_kernel(f16, with_law):
+    """F16_MATH_FAST hifi step: long runs are scheduled as (chunk of steps, group of 32 aircraft) items handed between
+    warps through global memory (no grid tail).  Same bits as one warp-task per group for all K steps: states, status
+    words and steps_done, with aircraft that leave the envelope at different times (xcg 0.35 open loop) and a ragged N."""
+    prev_mode = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        g = load_golden("xcg35")
+        n = 120_000 + 17
+        x, u = perturbed_trim(n, g["x_trim"], seed=3)
+        x[9, 5] = np.nan
+        u[1, 6] = np.nan
+        x[2, 7] = 99999.9       # leaves the altitude bound within a few steps
+        # 400 aircraft at full thrust just below the 900 ft/s bound: they cross it at different steps, i.e. in different chunks
+        x[6, 100:500] = np.linspace(880.0, 899.99, 400)
+        x[12, 100:500] = 19000.0
+        u[0, 100:500] = 19000.0
+        law = None
+        if with_law:
+            sel = list(g["mpc_x_idx"])
+            law = f16.make_lqr(-g["K_lqr"], sel, g["x_trim"][sel], g["u_trim"], rows=[1, 2, 3])
+        out = {}
+        for on in (0, 1):
+            prev = f16.lib.f16_set_step_chunking(on)
+            fb = f16.F16Batch(x, u, xcg=0.35)
+            fb.step(K=1500, lqr=law)
+            out[on] = (fb.x.copy(), fb.status.copy(), fb.steps_done.copy())
+            f16.lib.f16_set_step_chunking(prev)
+        assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+        assert np.array_equal(out[0][0], out[1][0], equal_nan=True)
+        st, done = out[1][1], out[1][2]
+        assert (st != 0).sum() > 100 and (st == 0).mean() > 0.5 and np.all(done[st == 0] == 1500) and np.all(done[st != 0] < 1500)
+        assert len(np.unique(done[st != 0] // 94)) > 3      # casualties spread over several chunks (chunk = 94 steps)
+    finally:
+        f16.lib.f16_set_math_mode(prev_mode)
+
+
 def test_step_freeze_policy(f16, oracle):
     g = load_golden("xcg35")
     x = np.repeat(g["x_trim"][:, None], 6, axis=1)
