@@ -7,9 +7,9 @@ this package loads that library and fails if it has not been built; there is no 
 from . import parameters
 from . import shard
 from ._lib import (CLR_AS_BUILT, CLR_FROM_FILE, FD_CENTRAL, FD_FORWARD, MATH_FAST, MATH_STRICT, F16Error, LqrLaw, init,
-                   lib)
+                   init_devices, lib, shutdown)
 from .plant import (F16Batch, atmos, discretise, dlqr, make_lqr, nlplant, reduce_jacobian, state_summary, state_summary_dev,
                     trim)
 
-__all__ = ["F16Batch", "F16Error", "LqrLaw", "atmos", "init", "lib", "make_lqr", "nlplant", "trim", "reduce_jacobian", "discretise", "dlqr", "state_summary", "state_summary_dev", "parameters",
+__all__ = ["F16Batch", "F16Error", "LqrLaw", "atmos", "init", "init_devices", "shutdown", "lib", "make_lqr", "nlplant", "trim", "reduce_jacobian", "discretise", "dlqr", "state_summary", "state_summary_dev", "parameters",
            "MATH_STRICT", "MATH_FAST", "CLR_AS_BUILT", "CLR_FROM_FILE", "FD_FORWARD", "FD_CENTRAL"]

@@ -13,7 +13,7 @@ c_ubp = ctypes.POINTER(ctypes.c_ubyte)
 c_ll = ctypes.c_longlong
 c_vp = ctypes.c_void_p
 
-F16_OK, F16_ERR_CUDA, F16_ERR_TABLES, F16_ERR_ARG, F16_ERR_NOINIT = 0, -1, -2, -3, -4
+F16_OK, F16_ERR_CUDA, F16_ERR_TABLES, F16_ERR_ARG, F16_ERR_NOINIT, F16_ERR_HOST = 0, -1, -2, -3, -4, -5
 MATH_STRICT, MATH_FAST = 0, 1
 CLR_AS_BUILT, CLR_FROM_FILE = 0, 1
 FD_FORWARD, FD_CENTRAL = 0, 1
@@ -52,6 +52,10 @@ def _load():
     L.f16_atmos.argtypes = [ctypes.c_double, ctypes.c_double, c_vp]
     L.f16_atmos.restype = None
     L.f16_init.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.f16_init_devices.argtypes = [ctypes.c_char_p, c_ip, ctypes.c_int]
+    L.f16_use_device.argtypes = [ctypes.c_int]
+    L.f16_set_host_pipeline.argtypes = [ctypes.c_int]
+    L.f16_shutdown.restype = None
     L.f16_last_error.restype = ctypes.c_char_p
     L.f16_set_default_xcg.argtypes = [ctypes.c_double]
     L.f16_set_default_xcg.restype = None
@@ -122,3 +126,19 @@ def init(table_path=None, device=-1):
     """f16_init: the packed blob shipped with the package unless told otherwise."""
     path = table_path if table_path is not None else (os.environ.get("F16_TABLE_PATH") or TABLE_BLOB)
     check(lib.f16_init(path.encode(), device), "f16_init")
+
+
+def init_devices(devices=None, table_path=None):
+    """f16_init_devices: one context per CUDA ordinal in `devices` (None = every visible GPU); the host-buffer batch calls then
+    split their aircraft over the contexts.  Returns the number of contexts."""
+    path = table_path if table_path is not None else (os.environ.get("F16_TABLE_PATH") or TABLE_BLOB)
+    if devices is None:
+        check(lib.f16_init_devices(path.encode(), None, 0), "f16_init_devices")
+    else:
+        arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        check(lib.f16_init_devices(path.encode(), arr, len(devices)), "f16_init_devices")
+    return lib.f16_device_count()
+
+
+def shutdown():
+    lib.f16_shutdown()

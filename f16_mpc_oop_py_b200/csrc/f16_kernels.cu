@@ -151,12 +151,13 @@ calc_xdot_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, l
 // ------------------------------------------------------------------------------------------------------
 // step_batch: K fused explicit-Euler steps of env.py::step, state in registers, optional fused LQR law
 // ------------------------------------------------------------------------------------------------------
-__constant__ LqrLaw c_lqr;
-
+// The law travels as a kernel parameter (constant bank, like a __constant__ symbol, but owned by the launch: nothing to upload,
+// nothing shared between launches, streams or devices).
 template <int FI, bool SMEM, bool LQR, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g,
-            long long ld_u, long long N, int K, double dt, int* __restrict__ status, int* __restrict__ steps_done) {
+            long long ld_u, long long N, int K, double dt, int* __restrict__ status, int* __restrict__ steps_done,
+            const __grid_constant__ LqrLaw c_lqr) {
   const double* img = acquire_tables<FI, SMEM>(tabs);
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
     const int own = owns<FI>(sel, n);
@@ -663,7 +664,7 @@ cudaError_t launch_calc_xdot(const LaunchCfg& cfg, const DevTables& tabs, const 
 }
 
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
-                          int*);
+                          int*, const LqrLaw);
 
 template <int FI, bool LQR>
 static StepKern pick_step(bool smem_tables, int& threads) {
@@ -682,10 +683,6 @@ cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const Batch
                         int* status, int* steps_done) {
   if (N <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
-  if (lqr_host) {
-    e = cudaMemcpyToSymbolAsync(c_lqr, lqr_host, sizeof(LqrLaw), 0, cudaMemcpyHostToDevice, cfg.stream);
-    if (e != cudaSuccess) return e;
-  }
   for (int FI = 1; FI >= 0 && e == cudaSuccess; FI--) {
     if (!wants(sel, FI)) continue;
     int threads = cfg.step_threads;
@@ -702,7 +699,8 @@ cudaError_t launch_step(const LaunchCfg& cfg, const DevTables& tabs, const Batch
     StepKern k = FI ? (lqr_host ? pick_step<1, true>(cfg.smem_tables, threads) : pick_step<1, false>(cfg.smem_tables, threads))
                     : (lqr_host ? pick_step<0, true>(cfg.smem_tables, threads) : pick_step<0, false>(cfg.smem_tables, threads));
     const int smem = FI ? table_smem<1>(cfg.smem_tables) : table_smem<0>(cfg.smem_tables);
-    e = launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+    e = launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done,
+                          lqr_host ? *lqr_host : LqrLaw());
   }
   return e;
 }

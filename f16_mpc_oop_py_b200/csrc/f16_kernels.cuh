@@ -106,6 +106,7 @@ cudaError_t launch_gather_f64(const LaunchCfg&, const double* src, long long ld_
 cudaError_t launch_scatter_f64(const LaunchCfg&, const double* src, long long ld_src, double* dst, long long ld_dst, int planes,
                                const unsigned* perm, long long N);
 cudaError_t launch_scatter_i32(const LaunchCfg&, const int* src, int* dst, const unsigned* perm, long long N);
+cudaError_t launch_fill_i32(const LaunchCfg&, int* dst, int value, long long N);
 int n_cta(long long N);
 }  // namespace partition
 

@@ -164,6 +164,16 @@ cudaError_t launch_scatter_i32(const LaunchCfg& cfg, const int* src, int* dst, c
   return cudaGetLastError();
 }
 
+__global__ void fill_i32_kernel(int* __restrict__ dst, int value, long long N) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) dst[n] = value;
+}
+cudaError_t launch_fill_i32(const LaunchCfg& cfg, int* dst, int value, long long N) {
+  if (N <= 0) return cudaSuccess;
+  fill_i32_kernel<<<move_grid(cfg, N), 256, 0, cfg.stream>>>(dst, value, N);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
 int n_cta(long long N) { return (int)((N + THREADS - 1) / THREADS); }
 
 }  // namespace partition

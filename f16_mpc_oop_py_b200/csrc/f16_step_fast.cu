@@ -12,7 +12,8 @@
 namespace f16 {
 namespace fast {
 
-__constant__ fastmath::LqrDense c_lqr_fast;
+// The closed-loop law (make_dense_law) travels as a kernel parameter of the launch: constant bank like a __constant__ symbol,
+// but nothing is uploaded, nothing is shared between launches, streams or devices, and no launch waits for an earlier one.
 
 // ------------------------------------------------------------------------------------------------------
 // step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
@@ -25,7 +26,7 @@ template <bool SMEM, bool LQR, int THREADS, int COLMASK = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 step_hifi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
                       const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
-                      int* __restrict__ status, int* __restrict__ steps_done) {
+                      int* __restrict__ status, int* __restrict__ steps_done, const __grid_constant__ fastmath::LqrDense c_lqr_fast) {
   const double* img = tabs.hifi_fast;
   if (SMEM) {
     stage_tables_tma<F16_FI_BYTES>(f16_smem, img, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
@@ -81,7 +82,8 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 template <bool LQR, int COLMASK>
 __global__ void __launch_bounds__(384, 1)
 step_hifi_fast_chunked_kernel(DevTables tabs, BatchSel sel, double* x_g, long long ld_x, const double* __restrict__ u_g, long long ld_u,
-                              long long N, int K, int chunk, double dt, int* status, int* steps_done, int* progress) {
+                              long long N, int K, int chunk, double dt, int* status, int* steps_done, int* progress,
+                              const __grid_constant__ fastmath::LqrDense c_lqr_fast) {
   stage_tables_tma<F16_FI_BYTES>(f16_smem, tabs.hifi_fast, reinterpret_cast<unsigned long long*>(f16_smem + F16_FI_BYTES));
   const double* img = reinterpret_cast<const double*>(f16_smem);
 #if defined(F16_FAST_LDS64)
@@ -133,7 +135,7 @@ template <bool LQR, int THREADS, int COLMASK = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 step_lofi_fast_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld_x,
                       const double* __restrict__ u_g, long long ld_u, long long N, int K, double dt,
-                      int* __restrict__ status, int* __restrict__ steps_done) {
+                      int* __restrict__ status, int* __restrict__ steps_done, const __grid_constant__ fastmath::LqrDense c_lqr_fast) {
   double* img = reinterpret_cast<double*>(f16_smem);
   for (int i = threadIdx.x; i < F16_LOFI_STEP_IMG_DOUBLES; i += THREADS)
     img[i] = i < F16_IMG_LOFI_DOUBLES ? tabs.lofi[i] : tabs.hifi_fast[F16_FI_POW + (i - F16_IMG_LOFI_DOUBLES)];
@@ -509,17 +511,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = [] {  // initialised once, thread-safe (the multi-device entry points launch from several threads)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      cudaGetLastError();
-  }
+      return reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -610,7 +609,7 @@ cudaError_t launch_fast_probe(const LaunchCfg& cfg, const DevTables& tabs, const
 }
 
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
-                          int*);
+                          int*, const fastmath::LqrDense);
 
 template <bool LQR>
 static StepKern pick_step_hifi_fast(bool smem_tables, int& threads) {
@@ -627,14 +626,9 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done) {
   if (N <= 0) return cudaSuccess;
-  if (lqr_host) {
-    static fastmath::LqrDense dense;  // caller holds the library mutex; the copy is enqueued before the launch below
-    cudaError_t e = cudaStreamSynchronize(cfg.stream);  // a previous launch may still read the symbol's source
-    if (e != cudaSuccess) return e;
-    fastmath::make_dense_law(*lqr_host, dense);
-    e = cudaMemcpyToSymbolAsync(c_lqr_fast, &dense, sizeof(dense), 0, cudaMemcpyHostToDevice, cfg.stream);
-    if (e != cudaSuccess) return e;
-  }
+  fastmath::LqrDense dense = fastmath::LqrDense();
+  if (lqr_host) fastmath::make_dense_law(*lqr_host, dense);
+  const bool mpc_cols = lqr_host && dense.colmask == F16_LQR_MPC_COLMASK;  // the reference's own column set: compile-time columns
   int threads = cfg.step_threads;
   // time-chunked scheduling (no grid tail): the default CTA size, a uniform hifi batch, enough steps to cut into chunks and
   // more than one round of warp-tasks; needs the status words (they carry "stopped" between chunks) and the progress flags
@@ -645,48 +639,30 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
     cudaError_t e = cudaMemsetAsync(cfg.step_progress, 0, (size_t)groups * 4, cfg.stream);
     if (e != cudaSuccess) return e;
     using ChunkKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, int, double, int*, int*,
-                               int*);
-    ChunkKern ck = step_hifi_fast_chunked_kernel<false, 0>;
-    if (lqr_host) {
-      fastmath::LqrDense d;
-      fastmath::make_dense_law(*lqr_host, d);
-      ck = d.colmask == F16_LQR_MPC_COLMASK ? step_hifi_fast_chunked_kernel<true, F16_LQR_MPC_COLMASK>
-                                            : step_hifi_fast_chunked_kernel<true, 0>;
-    }
+                               int*, const fastmath::LqrDense);
+    ChunkKern ck = !lqr_host ? step_hifi_fast_chunked_kernel<false, 0>
+                   : mpc_cols ? step_hifi_fast_chunked_kernel<true, F16_LQR_MPC_COLMASK>
+                              : step_hifi_fast_chunked_kernel<true, 0>;
     return launch_persistent(cfg, ck, 384, FAST_SMEM_BYTES, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, chunk, dt, status, steps_done,
-                             cfg.step_progress);
+                             cfg.step_progress, dense);
   }
   StepKern k = lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads);
-  if (lqr_host && cfg.smem_tables && threads == 384) {  // the reference's own column set at the default CTA size: compile-time columns
-    fastmath::LqrDense d;
-    fastmath::make_dense_law(*lqr_host, d);
-    if (d.colmask == F16_LQR_MPC_COLMASK) k = step_hifi_fast_kernel<true, true, 384, F16_LQR_MPC_COLMASK>;
-  }
+  if (mpc_cols && cfg.smem_tables && threads == 384) k = step_hifi_fast_kernel<true, true, 384, F16_LQR_MPC_COLMASK>;
   const int smem = cfg.smem_tables ? FAST_SMEM_BYTES : 0;
-  return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+  return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done, dense);
 }
 
-// the caller (launch_step) has uploaded nothing yet for the law: same symbol, same protocol as above
 cudaError_t launch_step_lofi_fast(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x,
                                   const double* u, long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host,
                                   int* status, int* steps_done) {
   if (N <= 0) return cudaSuccess;
-  if (lqr_host) {
-    static fastmath::LqrDense dense;
-    cudaError_t e = cudaStreamSynchronize(cfg.stream);
-    if (e != cudaSuccess) return e;
-    fastmath::make_dense_law(*lqr_host, dense);
-    e = cudaMemcpyToSymbolAsync(c_lqr_fast, &dense, sizeof(dense), 0, cudaMemcpyHostToDevice, cfg.stream);
-    if (e != cudaSuccess) return e;
-  }
+  fastmath::LqrDense dense = fastmath::LqrDense();
+  if (lqr_host) fastmath::make_dense_law(*lqr_host, dense);
   const int smem = F16_LOFI_STEP_IMG_DOUBLES * 8;
-  StepKern k = lqr_host ? step_lofi_fast_kernel<true, 384> : step_lofi_fast_kernel<false, 384>;
-  if (lqr_host) {  // the reference's own column set: compile-time columns (as in the hifi kernel)
-    fastmath::LqrDense d;
-    fastmath::make_dense_law(*lqr_host, d);
-    if (d.colmask == F16_LQR_MPC_COLMASK) k = step_lofi_fast_kernel<true, 384, F16_LQR_MPC_COLMASK>;
-  }
-  return launch_persistent(cfg, k, 384, smem, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done);
+  StepKern k = !lqr_host ? step_lofi_fast_kernel<false, 384>
+               : dense.colmask == F16_LQR_MPC_COLMASK ? step_lofi_fast_kernel<true, 384, F16_LQR_MPC_COLMASK>
+                                                      : step_lofi_fast_kernel<true, 384>;
+  return launch_persistent(cfg, k, 384, smem, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done, dense);
 }
 
 }  // namespace fast

@@ -32,6 +32,7 @@ extern "C" {
 #define F16_ERR_TABLES (-2)  /* aero tables not found or corrupt */
 #define F16_ERR_ARG (-3)     /* bad argument */
 #define F16_ERR_NOINIT (-4)  /* internal: initialisation failed earlier */
+#define F16_ERR_HOST (-5)    /* host memory or thread creation failed inside the library */
 
 /* ---- per-aircraft status word (int32, sticky within one call) ------------------------------------
  * The reference's behaviour in these cases is exit() (env.py:117-124) or undefined (mexndinterp.c:121-123);
@@ -99,10 +100,25 @@ void f16_atmos(double alt, double vt, double *coeff);
  * files, or NULL to search $F16_TABLE_PATH, <lib dir>/../data/f16_aero_v1.bin, ./C/.  device: CUDA ordinal,
  * or -1 for $F16_DEVICE / $LOCAL_RANK / 0.  Called implicitly (NULL, -1) by every other entry point. */
 int f16_init(const char *table_path, int device);
+/* Several GPUs of one box behind the same entry points.  One context -- stream, table images, scratch -- per entry
+ * of devices[0..ndev) (CUDA ordinals; NULL or ndev <= 0: every visible device; an ordinal may be listed more than once, which
+ * gives independent streams on that GPU).  From then on every HOST-buffer batch call (Nlplant_batch, calc_xdot_batch, step_batch,
+ * step_batch_traj, step_batch_stats, linearise_batch, trim_batch, state_summary_batch) cuts its N aircraft into contiguous
+ * slices, one per context (boundaries on multiples of 32 aircraft), and runs the slices concurrently, each from its own host
+ * thread with its own H2D / kernel / D2H pipeline: aircraft never interact, so nothing is exchanged between devices and the
+ * results are bit-identical to a single-device call.  Batches too small to feed every device use fewer of them.  The *_dev
+ * entry points, the memory helpers, the timers and the legacy symbols work on ONE context: the first, or the one selected by
+ * f16_use_device.  Must be the first call into the library (or follow f16_shutdown); f16_init is f16_init_devices with one entry. */
+int f16_init_devices(const char *table_path, const int *devices, int ndev);
+int f16_device_count(void);      /* number of contexts; 0 before init */
+int f16_use_device(int index);   /* context (index into the f16_init_devices list) of the *_dev entry points, the memory helpers
+                                    and the timers; returns the previous index or an F16_ERR_* code */
+int f16_set_host_pipeline(int on); /* 1 (default): the host-buffer batch calls run as a chunk pipeline on each device (H2D of chunk
+                                      c + 1 and D2H of chunk c - 1 under the kernels of chunk c); 0: one chunk.  Same bits. */
 void f16_shutdown(void);
 const char *f16_last_error(void);
 int f16_last_status(void);            /* status word of the last legacy Nlplant call */
-int f16_device(void);                 /* CUDA ordinal in use, -1 before init */
+int f16_device(void);                 /* CUDA ordinal of the current context, -1 before init */
 int f16_sm_count(void);
 int f16_set_math_mode(int mode);      /* F16_MATH_*; returns the previous mode */
 int f16_set_clr_mode(int mode);       /* F16_CLR_*; rebuilds the device tables; returns previous mode */
@@ -242,7 +258,7 @@ int f16_sync(void);
 void *f16_stream(void);            /* cudaStream_t the kernels run on */
 int f16_timer_start(void);         /* cudaEventRecord on f16_stream() */
 int f16_timer_stop(float *ms);     /* records, synchronises, returns elapsed ms */
-unsigned long long f16_launch_count(void); /* kernels of this library launched since init */
+unsigned long long f16_launch_count(void); /* kernels of this library launched since init (all contexts) */
 /* Sustained FP64 FMA rate of this GPU (TFLOP/s, 2 flop per DFMA) from a register-only DFMA kernel run for
  * about `ms` milliseconds: the measured denominator of the FP64 roofline. */
 int f16_measure_fp64_peak(double ms, double *tflops);

@@ -1,0 +1,120 @@
+"""The host-buffer entry points as pipelines of chunks and as slices over several device contexts (include/f16_b200.h:
+f16_init_devices, f16_set_host_pipeline).  Aircraft never interact, so neither the cut into chunks nor the
+cut into per-device slices may change a single bit of any per-aircraft result; the statistics rows are merged on the host by
+Chan's update and agree to rounding.  On a one-GPU box the slices run on two contexts of the same GPU (an ordinal may be listed
+twice), which exercises the same slicing, threading and merging code as two GPUs do."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from _inputs import perturbed_trim
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(n, seed=5):
+    g = load_golden("xcg25")
+    x, u = perturbed_trim(n, g["x_trim"], seed=seed, frac=0.05)
+    r = np.random.default_rng(seed)
+    fi = (r.uniform(size=n) < 0.7).astype(np.uint8)           # mixed hifi / lofi
+    xcg = np.where(r.uniform(size=n) < 0.5, 0.25, 0.35)
+    return x, u, fi, xcg
+
+
+def _run_all(f16, n_step, n_lin, n_trim):
+    """every sliced entry point once; returns a dict of outputs"""
+    out = {}
+    x, u, fi, xcg = _batch(n_step)
+    fb = f16.F16Batch(x, u, fi_flag=fi, xcg=xcg)
+    out["xdot"] = fb._calc_xdot(x, u)
+    out["xdot_st"] = fb.last_status.copy()
+    fb.step(K=3)
+    out["x3"], out["st3"], out["k3"] = fb.x.copy(), fb.status.copy(), fb.steps_done.copy()
+    fb.step(K=20)                                               # mixed batch, K >= 8: the fidelity partition on every chunk
+    out["x23"], out["st23"] = fb.x.copy(), fb.status.copy()
+    fb = f16.F16Batch(x, u, xcg=0.25)                           # uniform hifi, long run: the time-chunked step kernel
+    fb.step(K=600)
+    out["x600"], out["st600"] = fb.x.copy(), fb.status.copy()
+    out["nl"], out["nl_st"] = f16.nlplant(np.ascontiguousarray(x[:17]), fi=fi, xcg=xcg)
+    fb = f16.F16Batch(x[:, :n_lin], u[:, :n_lin], fi_flag=fi[:n_lin], xcg=xcg[:n_lin])
+    out["A"], out["B"], _, _ = fb.linearise(fb.x, fb.u, scheme="central")
+    out["lin_st"] = fb.last_status.copy()
+    fb = f16.F16Batch(x[:, :n_lin], u[:, :n_lin], xcg=0.35)
+    out["traj"] = fb.rollout(K=40, snap_every=10).copy()
+    out["traj_x"] = fb.x.copy()
+    fb = f16.F16Batch(x, u, xcg=0.35)
+    out["rows"] = fb.rollout_stats(K=40, snap_every=20).copy()
+    out["rows_x"] = fb.x.copy()
+    out["summary"] = f16.state_summary(fb.x, fb.status)
+    r = np.random.default_rng(3)
+    h, v = r.uniform(5000, 30000, n_trim), r.uniform(400, 800, n_trim)
+    xt, opt = f16.trim(h, v, tol=1e-10, maxiter=3000, xcg=0.35)
+    out["trim"], out["trim_fun"], out["trim_nit"], out["trim_st"] = xt, opt["fun"], opt["nit"], opt["status"]
+    return out
+
+
+EXACT = ["xdot", "xdot_st", "x3", "st3", "k3", "x23", "st23", "x600", "st600", "nl", "nl_st", "A", "B", "lin_st", "traj", "traj_x",
+         "rows_x", "trim", "trim_fun", "trim_nit", "trim_st"]
+
+
+def _compare(a, b):
+    for k in EXACT:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    for k in ("rows", "summary"):   # counts, min and max exactly; mean / M2 to rounding (another summation order)
+        ra, rb = np.asarray(a[k]).reshape(-1, 74), np.asarray(b[k]).reshape(-1, 74)
+        assert np.array_equal(ra[:, :38], rb[:, :38]), k
+        assert np.allclose(ra[:, 38:56], rb[:, 38:56], rtol=1e-12, atol=1e-300), k
+        assert np.allclose(ra[:, 56:], rb[:, 56:], rtol=1e-9, atol=1e-18), k
+
+
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_chunk_pipeline_does_not_change_a_bit(f16, math):
+    """300 001 aircraft (ragged: not a multiple of 32 or of the chunk size) = 4 chunks of the one-shot calls and of the K = 3
+    step, 1 of the K = 600 step; against the same calls as ONE chunk (f16_set_host_pipeline(0))."""
+    prev_math = f16.lib.f16_set_math_mode(f16.MATH_FAST if math == "fast" else f16.MATH_STRICT)
+    try:
+        prev = f16.lib.f16_set_host_pipeline(0)
+        one = _run_all(f16, 300_001, 40_003, 300)
+        f16.lib.f16_set_host_pipeline(1)
+        piped = _run_all(f16, 300_001, 40_003, 300)
+        f16.lib.f16_set_host_pipeline(prev)
+        _compare(one, piped)
+    finally:
+        f16.lib.f16_set_math_mode(prev_math)
+
+
+def test_slices_over_device_contexts_equal_one_context(f16):
+    """f16_init_devices: the same calls on one context and on 2 (and 3) contexts -- real GPUs where the box has them, else
+    contexts of the same GPU -- give the same bits."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    prev_math = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        assert f16.lib.f16_device_count() == 1
+        one = _run_all(f16, 200_003, 30_001, 5000)
+        for devs in ([0, 1 % ngpu], [0, 1 % ngpu, 2 % ngpu]):
+            f16.shutdown()
+            assert f16.lib.f16_device_count() == 0
+            assert f16.init_devices(devs) == len(devs)
+            # a second init on another list is refused, the same list is accepted
+            arr = (ctypes.c_int * 1)(0)
+            assert f16.lib.f16_init_devices(None, arr, 1) == -3
+            assert f16.init_devices(devs) == len(devs)
+            many = _run_all(f16, 200_003, 30_001, 5000)
+            _compare(one, many)
+            # the *_dev entry points follow f16_use_device
+            for i in range(len(devs)):
+                assert f16.lib.f16_use_device(i) >= 0
+                assert f16.lib.f16_device() == devs[i]
+                x, u, _, _ = _batch(4096, seed=9)
+                fb = f16.F16Batch(x, u, xcg=0.25)
+                s = f16.state_summary(fb.x, fb.status)
+                assert s[0] == 4096
+            assert f16.lib.f16_use_device(len(devs)) == -3
+            f16.lib.f16_use_device(0)
+    finally:
+        f16.shutdown()
+        f16.init()
+        f16.lib.f16_set_math_mode(prev_math)
