@@ -36,10 +36,12 @@ sys.path.insert(0, REPO)
 FLOP_PER_STEP = {"open": 750.0, "lqr": 815.0}   # algorithmic FP64 flop per hifi aircraft-step
 BYTES_PER_AIRCRAFT_LAUNCH = 320.0               # read 18 + 4, write 18 doubles, independent of K
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default workload (2^20 aircraft,
-# K = 10000), from the committed `ncu --set full` capture profiles/r01_step_hifi_fast_384_k10000_ncu_summary.md:
-# 194.72 MB read + 107.74 MB written (algorithmic 320 B x 2^20 = 335.5 MB + 4 MB of status words; part of the state was
-# still in L2 from the copy that precedes the launch).  Reported only when the run is that workload.
-NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 194_723_328 + 107_735_552}
+# K = 10000), from the committed `ncu --set full` capture profiles/r02_step_hifi_fast_chunked_k10000_ncu_summary.md:
+# 2.991 GB read + 2.423 GB written.  The time-chunked schedule (f16_step_fast.cu) passes the state through global memory
+# between its 16 chunks of 625 steps: 16 x (320 B x 2^20 + status and progress words) = 5.4 GB algorithmic for THIS schedule,
+# against 335.5 MB for the unchunked kernel (whose capture, r01, showed 302 MB) -- 0.19 % of the DRAM peak over the 352 ms
+# launch either way; the chunking buys the 3 % grid tail.  Reported only when the run is that workload.
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 2_990_819_000 + 2_423_162_000}
 
 # trim of the reference at 10000 ft / 700 ft/s, xcg 0.25, hifi (tests/golden/env_xcg25.npz, env.py:198-292)
 GOLDEN = os.path.join(REPO, "tests", "golden")
@@ -204,6 +206,37 @@ def measure_jacobians(L, ck, n, x_trim, u_trim, xcg, seed, scheme, reps=3):
             "flop_per_jacobian": 32300.0 if scheme else 17200.0, "out_bytes_per_jacobian": 396 * 8}
 
 
+def measure_cfg5(f16, L, ck, rank, n, ke, dt):
+    """BASELINE cfg 5 at its stated size: n (default 8 Mi) aircraft per GPU -- 64 Mi on eight --, closed loop u = u0 - K (x - x_trim)
+    fused into the step with the reference's own LQR gain (tests/golden K_lqr, env.py:344-358), hifi, xcg 0.35, +-5 % about
+    trim, ke Euler steps in ONE launch on resident inputs.  One timed launch (seconds long) after a small warm-up launch of the
+    same kernel; survivors counted on the device (f16_stats.cu)."""
+    from f16_mpc_oop_py_b200.shard import rank_seed
+    x_trim, u_trim, mpc_idx = trim_state("xcg35")
+    K = -np.load(os.path.join(GOLDEN, "env_xcg35.npz"))["K_lqr"]
+    law = f16.make_lqr(K, mpc_idx, x_trim[mpc_idx], u_trim, rows=[1, 2, 3])
+    x, u = perturbed_trim(n, x_trim, u_trim, seed=rank_seed(0xC5, rank))
+    d_x, d_u, d_st = L.f16_dev_alloc(x.nbytes), L.f16_dev_alloc(u.nbytes), L.f16_dev_alloc(4 * n)
+    if not (d_x and d_u and d_st):
+        raise RuntimeError("device allocation failed: " + L.f16_last_error().decode())
+    ck(L.f16_memcpy_h2d(d_x, x.ctypes.data, x.nbytes), "h2d")
+    ck(L.f16_memcpy_h2d(d_u, u.ctypes.data, u.nbytes), "h2d")
+    nw = min(n, 1 << 18)   # warm-up: the same kernel on a corner of the batch, then the state is restored
+    ck(L.step_batch_dev(d_x, n, d_u, n, nw, min(ke, 512), dt, ctypes.byref(law), None, 1, None, 0.35, d_st, None), "step_batch_dev")
+    ck(L.f16_memcpy_h2d(d_x, x.ctypes.data, x.nbytes), "h2d")
+    ck(L.f16_sync(), "sync")
+    launches0 = L.f16_launch_count()
+    ck(L.f16_timer_start(), "timer")
+    ck(L.step_batch_dev(d_x, n, d_u, n, n, ke, dt, ctypes.byref(law), None, 1, None, 0.35, d_st, None), "step_batch_dev")
+    ms = ctypes.c_float(0.0)
+    ck(L.f16_timer_stop(ctypes.byref(ms)), "timer")
+    launches = L.f16_launch_count() - launches0
+    row = f16.state_summary_dev(d_x, n, n, d_st)
+    for p in (d_x, d_u, d_st):
+        L.f16_dev_free(p)
+    return float(ms.value), row, int(launches)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -290,27 +323,38 @@ def run_ours(args):
     ck(L.f16_timer_stop(ctypes.byref(kms)), "timer")
     kernel_ms = float(kms.value)
 
-    # end-to-end through the host-buffer C ABI (what a ctypes user of the reference would call)
+    # end-to-end through the host-buffer C ABI (what a ctypes user of the reference would call): H2D + kernels + D2H inside the
+    # timed region, the call's own chunk pipeline overlapping them.  Twice: host arrays in pinned memory (f16_host_alloc_pinned)
+    # and in ordinary pageable NumPy arrays (what a caller who knows nothing about CUDA hands over).
     hx = L.f16_host_alloc_pinned(x.nbytes)
     hu = L.f16_host_alloc_pinned(u.nbytes)
     hs = L.f16_host_alloc_pinned(4 * n)
     px = np.frombuffer((ctypes.c_double * (18 * n)).from_address(hx), dtype=np.float64).reshape(18, n)
     pu = np.frombuffer((ctypes.c_double * (4 * n)).from_address(hu), dtype=np.float64).reshape(4, n)
-    e2e_ms, e2e_wall = [], []
-    for i in range(args.e2e_steps + 1):
-        px[:] = x
-        pu[:] = u
-        t0 = time.perf_counter()
-        ck(L.f16_timer_start(), "timer")   # CUDA events on the library stream bracket H2D + kernel + D2H of the call
-        ck(L.step_batch(hx, hu, n, ke, args.dt, law_p, None, 1, None, xcg, hs, None), "step_batch")
-        ems = ctypes.c_float(0.0)
-        ck(L.f16_timer_stop(ctypes.byref(ems)), "timer")
-        if i > 0:   # first call grows the library's device scratch
-            e2e_ms.append(float(ems.value))
-            e2e_wall.append(1e3 * (time.perf_counter() - t0))
+    gx, gu, gs = np.empty_like(x), np.empty_like(u), np.zeros(n, dtype=np.int32)
+
+    def e2e_samples(bx, bu, ax, au, a_st):
+        ms_l, wall_l = [], []
+        for i in range(args.e2e_steps + 1):
+            bx[:] = x
+            bu[:] = u
+            t0 = time.perf_counter()
+            ck(L.f16_timer_start(), "timer")   # CUDA events on the library stream bracket the whole call
+            ck(L.step_batch(ax, au, n, ke, args.dt, law_p, None, 1, None, xcg, a_st, None), "step_batch")
+            ems = ctypes.c_float(0.0)
+            ck(L.f16_timer_stop(ctypes.byref(ems)), "timer")
+            if i > 0:   # the first call grows the library's device scratch
+                ms_l.append(float(ems.value))
+                wall_l.append(1e3 * (time.perf_counter() - t0))
+        return ms_l, wall_l
+
+    e2e_ms, e2e_wall = e2e_samples(px, pu, hx, hu, hs) if args.e2e_steps > 0 else ([], [])
     e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
     e2e_wall_t = float(np.mean(e2e_wall)) if e2e_wall else float("nan")
-    e2e_equal = bool(np.array_equal(px, xf))
+    e2e_equal = bool(np.array_equal(px, xf)) if e2e_ms else None
+    pg_ms, pg_wall = e2e_samples(gx, gu, gx.ctypes.data, gu.ctypes.data, gs.ctypes.data) if args.e2e_steps > 0 else ([], [])
+    pg_t = float(np.mean(pg_ms)) if pg_ms else float("nan")
+    pg_equal = bool(np.array_equal(gx, xf)) if pg_ms else None
     for p in (hx, hu, hs):
         L.f16_host_free_pinned(p)
 
@@ -330,10 +374,19 @@ def run_ours(args):
                           "forward": measure_jacobians(L, ck, args.jac_points, x_trim, u_trim, xcg, rank_seed(0x1AC, rank), 0)}
             L.f16_set_linearise_variant(0)
 
+    cfg5 = None
+    if not args.no_cfg5 and args.workload == "open":
+        if dist:
+            dist.barrier()
+        cfg5 = measure_cfg5(f16, L, ck, rank, args.cfg5_aircraft, ke, args.dt)
+
     # max over ranks (timings are the slowest rank's); the only collective: end-of-run statistics
     from f16_mpc_oop_py_b200 import shard
     dev = f"cuda:{local}" if dist else "cpu"
-    elapsed_ms, kernel_ms, e2e_t = shard.max_over_ranks(dist, [elapsed_ms, kernel_ms, e2e_t], dev)
+    if cfg5:
+        c5_ms = shard.max_over_ranks(dist, [cfg5[0]], dev)[0]
+        c5_sum = shard.gather_summaries(dist, cfg5[1], dev)
+    elapsed_ms, kernel_ms, e2e_t, pg_t = shard.max_over_ranks(dist, [elapsed_ms, kernel_ms, e2e_t, pg_t], dev)
     # per-rank statistics reduced on the device (f16_stats.cu), then ONE all-gather of the 74-double rows
     summary = shard.gather_summaries(dist, f16.state_summary_dev(d_x, n, n, d_st), dev)
     alive = summary["alive_fraction"]
@@ -383,7 +436,11 @@ def run_ours(args):
             },
             "e2e": {"value": float(world) * n * ke / (e2e_t * 1e-3), "unit": "aircraft-steps/s",
                     "h2d_bytes_per_step": int(x.nbytes + u.nbytes), "d2h_bytes_per_step": int(x.nbytes + 4 * n),
-                    "ms_per_step": e2e_t, "host_wall_ms_per_step": e2e_wall_t, "bit_equal_to_device_path": e2e_equal},
+                    "ms_per_step": e2e_t, "host_wall_ms_per_step": e2e_wall_t, "bit_equal_to_device_path": e2e_equal,
+                    "samples": len(e2e_ms), "samples_ms": e2e_ms, "host_memory": "pinned (f16_host_alloc_pinned)",
+                    "pageable": {"value": float(world) * n * ke / (pg_t * 1e-3), "ms_per_step": pg_t, "samples": len(pg_ms),
+                                 "samples_ms": pg_ms, "bit_equal_to_device_path": pg_equal,
+                                 "host_memory": "ordinary NumPy arrays (pageable)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -398,6 +455,18 @@ def run_ours(args):
                     j["fp64_frac"] = j["value"] * j["flop_per_jacobian"] / 1e12 / peak_tf if peak_tf else None
                     j["kernel"] = "linearise_kernel (reference operation order, staged): f16_set_linearise_variant(2)"
                 line["jacobians"]["strict_build"] = jac_strict
+        if cfg5:
+            n5 = args.cfg5_aircraft
+            per_gpu = n5 * ke / (c5_ms * 1e-3)
+            line["cfg5_lqr"] = {
+                "workload": "cfg5: closed-loop LQR Monte Carlo (u = u0 - K (x - x_trim) fused into the step, the reference's K_lqr), "
+                            "hifi xcg 0.35, +-5% about trim",
+                "aircraft_per_gpu": n5, "aircraft_total": n5 * world, "euler_steps": ke, "value": per_gpu * world,
+                "unit": "aircraft-steps/s", "value_per_gpu": per_gpu, "ms_per_launch": c5_ms, "launches_per_gpu": cfg5[2],
+                "alive_fraction": c5_sum["alive_fraction"], "flop_per_aircraft_step": FLOP_PER_STEP["lqr"],
+                "fp64_frac": per_gpu * FLOP_PER_STEP["lqr"] / 1e12 / float(peak.value) if peak.value else None,
+                "timing": "one launch on resident inputs, CUDA events, max over ranks",
+            }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -421,9 +490,11 @@ def main():
     ap.add_argument("--math", default="fast", choices=["strict", "fast"])
     ap.add_argument("--step-threads", type=int, default=0)
     ap.add_argument("--no-table-staging", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed step_batch() calls per kind of host memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-jacobians", action="store_true", help="skip the linearise_batch (Jacobians/s) measurement")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg-5 leg (closed-loop LQR Monte Carlo at 8 Mi aircraft per GPU)")
+    ap.add_argument("--cfg5-aircraft", type=int, default=1 << 23, help="aircraft per GPU in the cfg-5 leg (8 Mi: 64 Mi on eight GPUs)")
     ap.add_argument("--jac-points", type=int, default=1 << 20,
                     help="trim points per GPU in the Jacobian measurement (SURVEY.md 8d: a 2^20-point batch for the throughput figure)")
     ap.add_argument("--lin-variant", type=int, default=None,

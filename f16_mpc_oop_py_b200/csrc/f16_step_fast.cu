@@ -632,9 +632,13 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   int threads = cfg.step_threads;
   // time-chunked scheduling (no grid tail): the default CTA size, a uniform hifi batch, enough steps to cut into chunks and
   // more than one round of warp-tasks; needs the status words (they carry "stopped" between chunks) and the progress flags
-  const long long groups = (N + 31) / 32;
+  // ... and a tail worth removing: with R = groups / (12 warps x SMs) rounds of warp-tasks the plain kernel idles
+  // (ceil(R) - R) / ceil(R) of the launch (2.9 % at 2^20 aircraft, 0.3 % at 2^23, where the plain kernel is the faster one:
+  // measured 2.68e10 against 2.60e10 aircraft-steps/s closed loop)
+  const long long groups = (N + 31) / 32, slots = 12LL * cfg.sm_count, full = (groups + slots - 1) / slots;
+  const bool tail = (full * slots - groups) * 100 > full * slots;  // more than 1 % idle
   if (cfg.step_chunking && cfg.smem_tables && threads > 256 && threads <= 384 && sel.fi == nullptr && K >= 512 && status &&
-      cfg.step_progress && groups <= cfg.step_progress_cap && groups > 12LL * cfg.sm_count) {
+      cfg.step_progress && groups <= cfg.step_progress_cap && groups > slots && tail) {
     const int chunk = (K + 15) / 16 < 64 ? 64 : (K + 15) / 16;
     cudaError_t e = cudaMemsetAsync(cfg.step_progress, 0, (size_t)groups * 4, cfg.stream);
     if (e != cudaSuccess) return e;

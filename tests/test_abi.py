@@ -90,12 +90,12 @@ def test_package_never_touches_the_oracle():
                 assert "f16_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "hostemu" not in txt or fn == "f16_model.cuh", fn
 
-def _build_c_example(tmp_path):
+def _build_c_example(tmp_path, name="cfg1_open_loop"):
     import subprocess
-    exe = str(tmp_path / "cfg1_open_loop")
+    exe = str(tmp_path / name)
     pkg = os.path.join(REPO, "f16_mpc_oop_py_b200")
     subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(REPO, "include"),
-                    os.path.join(REPO, "examples", "cfg1_open_loop.c"), "-o", exe, "-L" + pkg, "-lf16_b200",
+                    os.path.join(REPO, "examples", name + ".c"), "-o", exe, "-L" + pkg, "-lf16_b200",
                     "-Wl,-rpath," + pkg, "-lm"], check=True)
     return exe
 
@@ -105,9 +105,11 @@ def test_c_host_program_builds_against_the_header(tmp_path):
     import subprocess
     import torch
     exe = _build_c_example(tmp_path)
+    exe5 = _build_c_example(tmp_path, "cfg5_closed_loop_multi_gpu")
     if not torch.cuda.is_available():
-        r = subprocess.run([exe], capture_output=True, text=True)
-        assert r.returncode == 2 and "no CPU path" in r.stderr
+        for e in (exe, exe5):
+            r = subprocess.run([e], capture_output=True, text=True)
+            assert r.returncode == 2 and "no CPU path" in r.stderr
 
 
 @pytest.mark.gpu
@@ -118,3 +120,14 @@ def test_c_host_program_runs_cfg1(tmp_path):
     r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "matches the reference's 10 s trajectory" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_host_program_runs_cfg5_on_every_gpu(tmp_path):
+    """BASELINE cfg 5 from C: f16_init_devices (all GPUs of the box) -> trim_batch -> lqr_gain_batch -> ONE step_batch call with
+    the fused law over 300 000 aircraft, sliced over the device contexts by the library; flown open loop (part of the batch leaves the
+    envelope: xcg 0.35 is unstable) and closed loop (every aircraft stays inside), which is what the program checks"""
+    import subprocess
+    r = subprocess.run([_build_c_example(tmp_path, "cfg5_closed_loop_multi_gpu"), "300000", "10000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "closed loop holds the whole batch" in r.stdout
