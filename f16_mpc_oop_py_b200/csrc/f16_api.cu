@@ -57,9 +57,11 @@ struct Dev {
   double* pin = nullptr;      // [17 in | 18 out | 3 atmos in/out ...]
   double* pin_dev = nullptr;
   DevBuf b_in, b_in2, b_out, b_fi, b_xcg, b_st, b_st2, b_a, b_b, b_flush, b_l1, b_l2, b_l3, b_l4, b_l5, b_sum, b_perm, b_pscr, b_px, b_pu, b_pxcg, b_pst, b_pk, b_redo, b_prog;
+  DevBuf b_cx[2], b_cu[2], b_cxcg[2], b_cst[2], b_ck[2], b_co[2], b_cflag, b_ckl;  // survivor compaction (step_compacting)
   std::vector<DevBuf*> bufs() {
     return {&b_in, &b_in2, &b_out, &b_fi, &b_xcg, &b_st, &b_st2, &b_a, &b_b, &b_flush, &b_l1, &b_l2, &b_l3, &b_l4, &b_l5, &b_sum, &b_perm,
-            &b_pscr, &b_px, &b_pu, &b_pxcg, &b_pst, &b_pk, &b_redo, &b_prog};
+            &b_pscr, &b_px, &b_pu, &b_pxcg, &b_pst, &b_pk, &b_redo, &b_prog, &b_cx[0], &b_cx[1], &b_cu[0], &b_cu[1], &b_cxcg[0],
+            &b_cxcg[1], &b_cst[0], &b_cst[1], &b_ck[0], &b_ck[1], &b_co[0], &b_co[1], &b_cflag, &b_ckl};
   }
   void destroy() {  // tolerant of a half-built context (a failed init releases what it had created)
     if (ordinal < 0 || cudaSetDevice(ordinal) != cudaSuccess) { cudaGetLastError(); return; }
@@ -93,6 +95,7 @@ struct State {
   int lin_variant = 0;
   bool step_chunking = true;
   bool host_pipeline = true;   // chunked H2D / kernel / D2H overlap in the host-buffer entry points
+  bool compaction = false;     // long runs: survivors repacked between chunks of steps (step_compacting); opt-in
   std::atomic<double> default_xcg{0.25};
   std::atomic<int> last_status{0};
 };
@@ -214,6 +217,7 @@ int init_locked(const char* table_path, int device, const int* devices, int ndev
   if (const char* v = getenv("F16_TABLE_STAGING")) G.smem_tables = atoi(v) != 0;
   if (const char* v = getenv("F16_STEP_CHUNKING")) G.step_chunking = atoi(v) != 0;
   if (const char* v = getenv("F16_HOST_PIPELINE")) G.host_pipeline = atoi(v) != 0;
+  if (const char* v = getenv("F16_STEP_COMPACTION")) G.compaction = atoi(v) != 0;
   if (const char* v = getenv("F16_LIN_VARIANT")) G.lin_variant = (atoi(v) == 1 || atoi(v) == 2) ? atoi(v) : 0;
 
   for (int o : want) {
@@ -360,11 +364,40 @@ Chunks plan_chunks(long long n, long long min_chunk, int max_chunks) {
 
 // in(slot, lo, m, stream): enqueue the H2D of aircraft [lo, lo + m) of this call into `slot`; work(slot, lo, m): enqueue the kernels
 // on D->stream; out(slot, lo, m, stream): enqueue the D2H.  All three return F16_* codes.  Returns after everything has landed.
+// Issue order on the host: normally in(c), work(c), out(c - 1) -- work() only enqueues, and a pageable in(c + 1), which blocks
+// the host while the driver stages it, then runs under the kernels of chunk c.  With work_blocks (work() waits on the device:
+// the survivor counts of step_compacting) the copies either side of a chunk are enqueued BEFORE its work: in(c + 1), out(c - 1),
+// work(c).
 template <class In, class Work, class Out>
-int run_pipeline(long long n, const Chunks& ch, In in, Work work, Out out) {
+int run_pipeline(long long n, const Chunks& ch, bool work_blocks, In in, Work work, Out out) {
+  auto span = [&](int c, long long* lo, long long* m) {
+    *lo = (long long)c * ch.chunk;
+    *m = (n - *lo) < ch.chunk ? (n - *lo) : ch.chunk;
+  };
+  auto fetch = [&](int c) -> int {
+    const int s = c % 3;
+    long long lo, m;
+    span(c, &lo, &m);
+    if (c >= 3) CK(cudaStreamWaitEvent(D->s_in, D->e_out[s], 0));  // the slot is free once its previous result has left
+    const int rc = in(s, lo, m, D->s_in);
+    if (rc != F16_OK) return rc;
+    CK(cudaEventRecord(D->e_in[s], D->s_in));
+    return F16_OK;
+  };
+  auto run = [&](int c) -> int {
+    const int s = c % 3;
+    long long lo, m;
+    span(c, &lo, &m);
+    CK(cudaStreamWaitEvent(D->stream, D->e_in[s], 0));
+    const int rc = work(s, lo, m);
+    if (rc != F16_OK) return rc;
+    CK(cudaEventRecord(D->e_work[s], D->stream));
+    return F16_OK;
+  };
   auto flush = [&](int c) -> int {
     const int s = c % 3;
-    const long long lo = (long long)c * ch.chunk, m = (n - lo) < ch.chunk ? (n - lo) : ch.chunk;
+    long long lo, m;
+    span(c, &lo, &m);
     CK(cudaStreamWaitEvent(D->s_out, D->e_work[s], 0));
     const int rc = out(s, lo, m, D->s_out);
     if (rc != F16_OK) return rc;
@@ -372,16 +405,19 @@ int run_pipeline(long long n, const Chunks& ch, In in, Work work, Out out) {
     return F16_OK;
   };
   int rc = F16_OK;
-  for (int c = 0; c < ch.count && rc == F16_OK; c++) {
-    const int s = c % 3;
-    const long long lo = (long long)c * ch.chunk, m = (n - lo) < ch.chunk ? (n - lo) : ch.chunk;
-    if (c >= 3) CK(cudaStreamWaitEvent(D->s_in, D->e_out[s], 0));  // the slot is free once its previous result has left
-    if ((rc = in(s, lo, m, D->s_in)) != F16_OK) break;
-    CK(cudaEventRecord(D->e_in[s], D->s_in));
-    CK(cudaStreamWaitEvent(D->stream, D->e_in[s], 0));
-    if ((rc = work(s, lo, m)) != F16_OK) break;
-    CK(cudaEventRecord(D->e_work[s], D->stream));
-    if (c >= 1) rc = flush(c - 1);
+  if (work_blocks) {
+    rc = fetch(0);
+    for (int c = 0; c < ch.count && rc == F16_OK; c++) {
+      if (c + 1 < ch.count) rc = fetch(c + 1);  // slot (c + 1) mod 3 held chunk c - 2, flushed one iteration ago
+      if (rc == F16_OK && c >= 1) rc = flush(c - 1);
+      if (rc == F16_OK) rc = run(c);
+    }
+  } else {
+    for (int c = 0; c < ch.count && rc == F16_OK; c++) {
+      rc = fetch(c);
+      if (rc == F16_OK) rc = run(c);
+      if (rc == F16_OK && c >= 1) rc = flush(c - 1);
+    }
   }
   if (rc == F16_OK) rc = flush(ch.count - 1);
   // drain all three streams whatever happened: the caller's buffers must not be touched after the call returns
@@ -591,6 +627,13 @@ int f16_set_step_chunking(int on) {
   std::lock_guard<std::mutex> lk(G_mu);
   int prev = G.step_chunking ? 1 : 0;
   G.step_chunking = on != 0;
+  return prev;
+}
+
+int f16_set_step_compaction(int on) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.compaction ? 1 : 0;
+  G.compaction = on != 0;
   return prev;
 }
 
@@ -833,7 +876,7 @@ static int xdot_host(const double* x, const double* u, double* xdot, long long l
   auto os = [&](int s) { return (double*)D->b_out.p + (size_t)s * 18 * cs; };
   auto ss = [&](int s) { return (int*)D->b_st.p + (size_t)s * cs; };
   return run_pipeline(
-      n, ch,
+      n, ch, false,
       [&](int s, long long c, long long m, cudaStream_t st) -> int {
         CK(planes_h2d(xs(s), x + lo + c, ld, m, NX, st));
         if (u) CK(planes_h2d(us(s), u + lo + c, ld, m, 4, st));
@@ -876,6 +919,106 @@ int calc_xdot_batch(const double* x_soa, const double* u_soa, double* xdot_soa, 
   });
 }
 
+// A Monte-Carlo run with casualties (BASELINE cfg 5 without the regulator; xcg 0.35 open loop loses half of a +-5 % batch within
+// 10 s).  An aircraft that leaves the envelope is frozen and keeps its lane; deaths are scattered, so nearly every warp keeps a
+// survivor and runs all K steps: the launch lasts as long as if nobody had died.  Here a long run is cut into eight chunks of
+// steps (step_batch is restartable bit for bit at any step boundary); after a chunk the survivors are counted, and once more
+// than 1/16 of the active lanes idle, the active set is reordered -- survivors first (stable partition of f16_partition.cu on
+// the status words, gather of the 23 planes), the newly stopped aircraft scattered to their final place in the caller's arrays
+// -- and the next chunk runs on the survivors only, in full warps.  Per-aircraft results are the same bits as one launch of K
+// steps.  Without casualties the cost is the chunking (the launches drain and refill the GPU): chunks double while nobody is
+// lost, three extra launches for a clean 10^4-step run.  Opt-in: f16_set_step_compaction(1).
+static int step_compacting(double* d_x, long long ld_x, const double* d_u, long long ld_u, long long N, int K, double dt,
+                           const f16_lqr_t* lqr, int fi, const double* d_xcg, double xcg_default, int* d_st, int* d_k, bool smem) {
+  const size_t n = (size_t)N;
+  const int n_cta = f16::partition::n_cta(N);
+  CK(D->b_ckl.reserve(n * 4));
+  CK(D->b_cflag.reserve(n));
+  CK(D->b_perm.reserve(n * 4));
+  CK(D->b_pscr.reserve((size_t)n_cta * 6 * 4 + 64));
+  if (!d_k) CK(D->b_pk.reserve(n * 4));  // the step counts are kept even when the caller does not ask for them
+  int* kl = (int*)D->b_ckl.p;
+  unsigned char* flag = (unsigned char*)D->b_cflag.p;
+  unsigned* perm = (unsigned*)D->b_perm.p;
+  unsigned* scr = (unsigned*)D->b_pscr.p;
+  long long* totals_dev = (long long*)(scr + (size_t)n_cta * 6 + 2);
+  long long* tot = reinterpret_cast<long long*>(D->pin + 56);
+  const f16::LqrLaw* law = reinterpret_cast<const f16::LqrLaw*>(lqr);
+  const f16::LaunchCfg c = cfg(smem);
+
+  // the working view: the caller's arrays until the first reorder, then one of the two scratch sets
+  double* x = d_x;
+  const double* u = d_u;
+  const double* xcg = d_xcg;
+  long long ldx = ld_x, ldu = ld_u;
+  int* st = d_st;
+  int* ktot = d_k ? d_k : (int*)D->b_pk.p;
+  const unsigned* orig = nullptr;  // working slot -> aircraft index (identity while on the caller's arrays)
+  int set = -1;
+  long long n_act = N;
+  CK(cudaMemsetAsync(ktot, 0xff, n * 4, D->stream));  // -1: still flying
+  // chunks of K / 8 steps while aircraft are being lost; every chunk that loses nobody doubles the next one
+  const int chunk0 = (K + 7) / 8;
+  int chunk = chunk0, base = 0;
+  long long idle_before = 0;  // stopped aircraft still inside the active set
+  while (base < K) {
+    const int kc = (K - base) < chunk ? (K - base) : chunk;
+    CK(DISPATCH(launch_step, c, tabs(), sel_of(nullptr, fi, xcg, xcg_default), x, ldx, u, ldu, n_act, kc, dt, law, st, kl));
+    CK(f16::partition::launch_mark_survivors(c, st, kl, ktot, base, n_act, flag));
+    base += kc;
+    if (base >= K) break;
+    CK(f16::partition::launch_build(c, flag, n_act, perm, totals_dev, scr));
+    CK(cudaMemcpyAsync(tot, totals_dev, 3 * sizeof(long long), cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    const long long n_alive = tot[0], n_dead = n_act - n_alive;
+    if (n_alive == 0) break;
+    chunk = n_dead == idle_before ? (chunk < K ? 2 * chunk : chunk) : chunk0;
+    idle_before = n_dead;
+    if (n_dead * 16 < n_act) continue;  // fewer than 1/16 of the active lanes idle: not worth a reorder yet
+    idle_before = 0;
+    const int nx = set < 0 ? 0 : 1 - set;
+    const size_t m = (size_t)n_act;
+    CK(D->b_cx[nx].reserve(18 * m * 8));
+    CK(D->b_cu[nx].reserve(4 * m * 8));
+    CK(D->b_cst[nx].reserve(m * 4));
+    CK(D->b_co[nx].reserve(m * 4));
+    if (d_xcg) CK(D->b_cxcg[nx].reserve(m * 8));
+    CK(D->b_ck[nx].reserve(m * 4));
+    double* xn = (double*)D->b_cx[nx].p;
+    double* un = (double*)D->b_cu[nx].p;
+    int* stn = (int*)D->b_cst[nx].p;
+    int* kn = (int*)D->b_ck[nx].p;
+    unsigned* on = (unsigned*)D->b_co[nx].p;
+    CK(f16::partition::launch_gather_f64(c, x, ldx, xn, n_act, 18, perm, n_act));
+    CK(f16::partition::launch_gather_f64(c, u, ldu, un, n_act, 4, perm, n_act));
+    if (d_xcg) CK(f16::partition::launch_gather_f64(c, xcg, n_act, (double*)D->b_cxcg[nx].p, n_act, 1, perm, n_act));
+    CK(f16::partition::launch_gather_i32(c, st, stn, perm, n_act));
+    CK(f16::partition::launch_gather_i32(c, ktot, kn, perm, n_act));
+    if (orig) CK(f16::partition::launch_gather_i32(c, (const int*)orig, (int*)on, perm, n_act));
+    else CK(cudaMemcpyAsync(on, perm, m * 4, cudaMemcpyDeviceToDevice, D->stream));
+    // the aircraft that stopped since the last reorder sit in [n_alive, n_act): they go to their final place now
+    CK(f16::partition::launch_scatter_f64(c, xn + n_alive, n_act, d_x, ld_x, 18, on + n_alive, n_dead));
+    CK(f16::partition::launch_scatter_i32(c, stn + n_alive, d_st, on + n_alive, n_dead));
+    if (d_k) CK(f16::partition::launch_scatter_i32(c, kn + n_alive, d_k, on + n_alive, n_dead));
+    x = xn; ldx = n_act;
+    u = un; ldu = n_act;
+    xcg = d_xcg ? (const double*)D->b_cxcg[nx].p : nullptr;
+    st = stn;
+    ktot = kn;
+    orig = on;
+    set = nx;
+    n_act = n_alive;
+  }
+  // the end: whoever never stopped has taken all K steps; a reordered working set goes back to the caller's arrays
+  CK(f16::partition::launch_close_steps(c, ktot, K, n_act));
+  if (set >= 0) {
+    CK(f16::partition::launch_scatter_f64(c, x, ldx, d_x, ld_x, 18, orig, n_act));
+    CK(f16::partition::launch_scatter_i32(c, st, d_st, orig, n_act));
+    if (d_k) CK(f16::partition::launch_scatter_i32(c, ktot, d_k, orig, n_act));
+  }
+  return F16_OK;
+}
+
 // the fused step on device arrays of the context D: mixed batches through the fidelity partition, the rest directly; tables go
 // to shared memory whenever the launch does real work, a handful of aircraft-steps read them via L2
 static int step_on_device(double* d_x, long long ld_x, const double* d_u, long long ld_u, long long n, int K, double dt,
@@ -887,6 +1030,8 @@ static int step_on_device(double* d_x, long long ld_x, const double* d_u, long l
   if (rc != F16_OK || handled) return rc;
   if (uniform >= 0) { d_fi = nullptr; fi_default = uniform; }  // every flag says the same: no partition, no per-lane masking
   const bool smem = G.smem_tables && (n * (long long)(K > 0 ? K : 1) >= 4096);
+  if (G.compaction && !d_fi && d_st && K >= 4096 && n >= 65536 && n < (1LL << 31) && (fi_default == 0 || fi_default == 1))
+    return step_compacting(d_x, ld_x, d_u, ld_u, n, K, dt, lqr, fi_default, d_xcg, xcg_default, d_st, d_k, smem);
   CK(DISPATCH(launch_step, cfg(smem), tabs(), sel_of(d_fi, fi_default, d_xcg, xcg_default), d_x, ld_x, d_u, ld_u, n, K, dt,
               reinterpret_cast<const f16::LqrLaw*>(lqr), d_st, d_k));
   return F16_OK;
@@ -913,7 +1058,7 @@ static int step_host(double* x, const double* u, long long ld, long long lo, lon
   auto ss = [&](int s) { return (int*)D->b_st.p + (size_t)s * cs; };
   auto ks = [&](int s) { return (int*)D->b_st2.p + (size_t)s * cs; };
   return run_pipeline(
-      n, ch,
+      n, ch, G.compaction && K >= 4096,
       [&](int s, long long c, long long m, cudaStream_t st) -> int {
         CK(planes_h2d(xs(s), x + lo + c, ld, m, 18, st));
         CK(planes_h2d(us(s), u + lo + c, ld, m, 4, st));
@@ -1024,7 +1169,7 @@ static int linearise_host(const double* x, const double* u, long long ld, long l
   auto bs = [&](int s) { return (double*)D->b_b.p + (size_t)s * 72 * cs; };
   auto ss = [&](int s) { return (int*)D->b_st.p + (size_t)s * cs; };
   return run_pipeline(
-      n, ch,
+      n, ch, false,
       [&](int s, long long c, long long m, cudaStream_t st) -> int {
         CK(planes_h2d(xs(s), x + lo + c, ld, m, 18, st));
         CK(planes_h2d(us(s), u + lo + c, ld, m, 4, st));
@@ -1114,7 +1259,7 @@ int trim_batch(const double* h, const double* V, long long N, double tol, int ma
 }
 
 // ---- end-of-run statistics, reduced on the device (f16_stats.cu) ------------------------------------------------------
-// enqueue the four reduction kernels; row_dev (74 doubles) must not alias the scratch (56 doubles per CTA column)
+// enqueue the two reduction kernels; row_dev (74 doubles) must not alias the scratch (PARTIAL_STRIDE doubles per CTA column)
 static int enqueue_summary(const double* d_x, long long ld, long long N, const int* d_status, double* row_dev, double* scratch,
                            int grid) {
   CK(f16::stats::launch_summary(cfg(false), d_x, ld, N, d_status, row_dev, scratch, grid));
@@ -1123,9 +1268,9 @@ static int enqueue_summary(const double* d_x, long long ld, long long N, const i
 
 static int summary_common(const double* d_x, long long ld, long long N, const int* d_status, double* row_host) {
   const int grid = f16::stats::summary_grid(cfg(false), N);
-  CK(D->b_sum.reserve(((size_t)grid * 56 + 80) * 8));
+  CK(D->b_sum.reserve(((size_t)grid * f16::stats::PARTIAL_STRIDE + 80) * 8));
   double* scratch = (double*)D->b_sum.p;
-  double* row = scratch + (size_t)grid * 56;
+  double* row = scratch + (size_t)grid * f16::stats::PARTIAL_STRIDE;
   int rc = enqueue_summary(d_x, ld, N, d_status, row, scratch, grid);
   if (rc != F16_OK) return rc;
   D2H(row_host, row, 74 * 8);
@@ -1138,9 +1283,9 @@ static int step_stats_core(double* d_x, long long ld_x, const double* d_u, long 
                            double dt, const f16_lqr_t* lqr, const f16::BatchSel& sel, int* d_status, double* rows_host) {
   const int n_rows = K / snap_every;
   const int grid = f16::stats::summary_grid(cfg(false), N);
-  CK(D->b_sum.reserve(((size_t)grid * 56 + (size_t)(n_rows > 0 ? n_rows : 1) * 74 + 8) * 8));
+  CK(D->b_sum.reserve(((size_t)grid * f16::stats::PARTIAL_STRIDE + (size_t)(n_rows > 0 ? n_rows : 1) * 74 + 8) * 8));
   double* scratch = (double*)D->b_sum.p;
-  double* rows_dev = scratch + (size_t)grid * 56;
+  double* rows_dev = scratch + (size_t)grid * f16::stats::PARTIAL_STRIDE;
   const bool smem = G.smem_tables && (N * (long long)snap_every >= 4096);
   int done = 0, snap = 0;
   while (done < K) {

@@ -92,6 +92,7 @@ cudaError_t launch_dlqr(const LaunchCfg&, const double* Ad, const double* Bd, co
 
 // f16_stats.cu: per-state summary of a batch (count, alive, min, max, mean, M2), reduced on the device
 namespace stats {
+constexpr int PARTIAL_STRIDE = 80;  // doubles of device scratch per CTA column of the reduction (73 used)
 cudaError_t launch_summary(const LaunchCfg&, const double* x, long long ld, long long N, const int* status, double* row,
                            double* scratch, int grid);
 int summary_grid(const LaunchCfg&, long long N);
@@ -107,6 +108,10 @@ cudaError_t launch_scatter_f64(const LaunchCfg&, const double* src, long long ld
                                const unsigned* perm, long long N);
 cudaError_t launch_scatter_i32(const LaunchCfg&, const int* src, int* dst, const unsigned* perm, long long N);
 cudaError_t launch_fill_i32(const LaunchCfg&, int* dst, int value, long long N);
+cudaError_t launch_gather_i32(const LaunchCfg&, const int* src, int* dst, const unsigned* perm, long long N);
+cudaError_t launch_mark_survivors(const LaunchCfg&, const int* status, const int* k_launch, int* k_total, int base, long long N,
+                                  unsigned char* flag);
+cudaError_t launch_close_steps(const LaunchCfg&, int* k_total, int K, long long N);
 int n_cta(long long N);
 }  // namespace partition
 

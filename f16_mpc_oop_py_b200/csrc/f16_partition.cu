@@ -174,6 +174,43 @@ cudaError_t launch_fill_i32(const LaunchCfg& cfg, int* dst, int value, long long
   return cudaGetLastError();
 }
 
+cudaError_t launch_gather_i32(const LaunchCfg& cfg, const int* src, int* dst, const unsigned* perm, long long N) {
+  if (N <= 0) return cudaSuccess;
+  move_kernel<int, true><<<move_grid(cfg, N), 256, 0, cfg.stream>>>(src, N, dst, N, 1, perm, N);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
+// ---- survivors of a Monte-Carlo run (f16_api.cu: step_compacting) -------------------------------------------------------
+// after a chunk of k_launch[n] steps that started at step `base`: flag[n] = 1 for an aircraft still flying (status 0), 0 for one
+// that has stopped; k_total[n] (< 0 = still flying) records the step at which an aircraft stopped, once
+__global__ void mark_kernel(const int* __restrict__ status, const int* __restrict__ k_launch, int* __restrict__ k_total, int base,
+                            long long N, unsigned char* __restrict__ flag) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const bool flying = status[n] == 0;
+    flag[n] = flying ? 1 : 0;
+    if (!flying && k_total[n] < 0) k_total[n] = base + k_launch[n];
+  }
+}
+cudaError_t launch_mark_survivors(const LaunchCfg& cfg, const int* status, const int* k_launch, int* k_total, int base, long long N,
+                                  unsigned char* flag) {
+  if (N <= 0) return cudaSuccess;
+  mark_kernel<<<move_grid(cfg, N), 256, 0, cfg.stream>>>(status, k_launch, k_total, base, N, flag);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+// end of the run: an aircraft that never stopped has taken all K steps
+__global__ void close_steps_kernel(int* __restrict__ k_total, int K, long long N) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x)
+    if (k_total[n] < 0) k_total[n] = K;
+}
+cudaError_t launch_close_steps(const LaunchCfg& cfg, int* k_total, int K, long long N) {
+  if (N <= 0) return cudaSuccess;
+  close_steps_kernel<<<move_grid(cfg, N), 256, 0, cfg.stream>>>(k_total, K, N);
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+  return cudaGetLastError();
+}
+
 int n_cta(long long N) { return (int)((N + THREADS - 1) / THREADS); }
 
 }  // namespace partition

@@ -4,11 +4,18 @@
 //     [n, alive, min[18], max[18], mean[18], M2[18]]
 // is what a rank contributes to the only collective of a run (an all-gather of these rows, shard.py::merge_summaries).
 //
-// HBM-bound: every plane of the SoA state and the status words are read once per pass, 148 B per aircraft, fully
-// coalesced (thread n reads x[i][n]; the status words are read by both state halves); two passes (sums -> mean, then squared deviations about that mean: no cancellation)
-// = 296 B per aircraft, the second one mostly out of L2 for batches below ~0.8 Mi aircraft.  Reductions are a fixed
-// tree (per thread -> warp shuffles -> shared memory -> one partial per CTA -> one finishing CTA, lane-strided), so the
-// result is bit-reproducible for a given device and batch size; no atomics.
+// HBM-bound, ONE pass: every plane of the SoA state is read once and the status words three times (once per group of six
+// states), 152 B per aircraft, fully coalesced (thread n reads x[i][n]).  Mean and M2 come out of the same pass without
+// cancellation by the textbook shifted-data form: with a shift c_i taken from INSIDE the data -- state i of the first
+// surviving aircraft among the first 32 of the batch (aircraft 0 if none survives there) -- the kernel accumulates
+// S1 = sum (v - c) and S2 = sum (v - c)^2, which add up exactly like plain sums over threads, warps and CTAs, and the finishing
+// CTA forms mean = c + S1 / n, M2 = S2 - S1^2 / n.  The subtraction v - c is exact for values within a factor of two of c and
+// the final difference loses (|mean - c| / sigma)^2 ulps: nothing for a shift inside the cloud, 1e-10 relative only when that
+// one aircraft sits a thousand standard deviations out.  (Combining per-thread MEANS by Chan's update is first-order in the
+// rounding of those means and misses 1e-10 on a plane like h = 10000 +- 0.001 ft; two passes -- sums, then squared deviations
+// about the mean, the round-1 kernel -- cost twice the bytes: 0.119 ms at 2^20 aircraft.)  Reductions are a fixed tree
+// (per thread -> warp shuffles -> shared memory -> one partial per CTA -> one finishing CTA, lane-strided), so the result is
+// bit-reproducible for a given device and batch size; no atomics.
 #include <math.h>
 #include <stdint.h>
 
@@ -36,26 +43,36 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// pass 1: partial[b] = {sum[18], min[18], max[18], alive count} of CTA column b   (55 doubles, stride 56)
-// pass 2: partial[b] = {sum (x - mean)^2 [18]}                                    (18 doubles, stride 56)
-// blockIdx.y picks nine of the eighteen states: 27 accumulators per thread instead of 54 keep three CTAs resident per SM
-// (the loads in flight, not the arithmetic, set the pace).
-constexpr int NH = NS / 2;
-template <int PASS>
-__global__ void __launch_bounds__(THREADS, 3)
-partial_kernel(const double* __restrict__ x, long long ld, long long N, const int* __restrict__ status,
-               const double* __restrict__ row /* pass 2: the row with the means filled in */, double* __restrict__ partial) {
-  __shared__ double red[THREADS / 32][3 * NH + 1];
-  const int s0 = blockIdx.y * NH;  // first state of this half
+// partial[b] of CTA column b (stride PARTIAL_STRIDE): S1[18] | S2[18] | min[18] | max[18] | alive count
+// blockIdx.y picks NS / NG of the eighteen states (six: 24 accumulators + 6 shifts per thread); the loads in flight, not the
+// arithmetic, set the pace.
+
+// the common shift: state s of the first aircraft with status 0 among the first min(N, 32), else of aircraft 0
+__device__ __forceinline__ long long shift_aircraft(const int* __restrict__ status, long long N) {
+  const int lane = threadIdx.x & 31;
+  const bool ok = lane < N && (!status || status[lane] == 0);
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  return m ? (long long)(__ffs(m) - 1) : 0;
+}
+
+template <int NG, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+partial_kernel(const double* __restrict__ x, long long ld, long long N, const int* __restrict__ status, double* __restrict__ partial) {
+  constexpr int NH = NS / NG;
+  __shared__ double red[THREADS / 32][4 * NH + 1];
+  const int s0 = blockIdx.y * NH;  // first state of this group
   x += (long long)s0 * ld;
-  double s[NH], mn[NH], mx[NH], mean[NH];
+  const long long j0 = N > 0 ? shift_aircraft(status, N) : 0;
+  double c[NH], s1[NH], s2[NH], mn[NH], mx[NH];
   double cnt = 0.0;
 #pragma unroll
   for (int i = 0; i < NH; i++) {
-    s[i] = 0.0;
+    const double v0 = N > 0 ? x[i * ld + j0] : 0.0;
+    c[i] = fabs(v0) < INFINITY ? v0 : 0.0;  // a NaN or an infinity is no shift
+    s1[i] = 0.0;
+    s2[i] = 0.0;
     mn[i] = INFINITY;
     mx[i] = -INFINITY;
-    mean[i] = PASS == 2 ? row[38 + s0 + i] : 0.0;
   }
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
     if (status && status[n] != 0) continue;
@@ -63,59 +80,56 @@ partial_kernel(const double* __restrict__ x, long long ld, long long N, const in
 #pragma unroll
     for (int i = 0; i < NH; i++) {
       const double v = x[i * ld + n];
-      if (PASS == 1) {
-        s[i] += v;
-        mn[i] = v < mn[i] ? v : mn[i];  // a NaN never wins a comparison: skipped, as fmin / fmax would
-        mx[i] = v > mx[i] ? v : mx[i];
-      } else {
-        const double d = v - mean[i];
-        s[i] = fma(d, d, s[i]);
-      }
+      const double d = v - c[i];
+      s1[i] += d;
+      s2[i] = fma(d, d, s2[i]);
+      mn[i] = v < mn[i] ? v : mn[i];  // a NaN never wins a comparison: skipped, as fmin / fmax would
+      mx[i] = v > mx[i] ? v : mx[i];
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   cnt = warp_sum(cnt);
-  if (lane == 0) red[warp][3 * NH] = cnt;
+  if (lane == 0) red[warp][4 * NH] = cnt;
 #pragma unroll
   for (int i = 0; i < NH; i++) {
-    const double a = warp_sum(s[i]);
-    if (lane == 0) red[warp][i] = a;
-    if (PASS == 1) {
-      const double b = warp_min(mn[i]), c = warp_max(mx[i]);
-      if (lane == 0) {
-        red[warp][NH + i] = b;
-        red[warp][2 * NH + i] = c;
-      }
+    const double a = warp_sum(s1[i]), q = warp_sum(s2[i]), lo = warp_min(mn[i]), hi = warp_max(mx[i]);
+    if (lane == 0) {
+      red[warp][i] = a;
+      red[warp][NH + i] = q;
+      red[warp][2 * NH + i] = lo;
+      red[warp][3 * NH + i] = hi;
     }
   }
   __syncthreads();
-  const int nfield = PASS == 1 ? 3 * NH + 1 : NH;
-  if (threadIdx.x < nfield) {
-    const int f = threadIdx.x, kind = f / NH;  // 0 sum, 1 min, 2 max, 3 count
+  if (threadIdx.x < 4 * NH + 1) {
+    const int f = threadIdx.x, kind = f / NH;  // 0 S1, 1 S2, 2 min, 3 max, 4 count
     double a = red[0][f];
     for (int w = 1; w < THREADS / 32; w++) {
       const double b = red[w][f];
-      a = (PASS == 1 && kind == 1) ? fmin(a, b) : (PASS == 1 && kind == 2) ? fmax(a, b) : a + b;
+      a = kind == 2 ? fmin(a, b) : kind == 3 ? fmax(a, b) : a + b;
     }
-    // field layout of a partial: sum[18] | min[18] | max[18] | count
-    const int dst = kind == 3 ? 3 * NS : kind * NS + s0 + (f - kind * NH);
-    if (kind != 3 || blockIdx.y == 0) partial[(long long)blockIdx.x * 56 + dst] = a;
+    const int dst = kind == 4 ? 4 * NS : kind * NS + s0 + (f - kind * NH);
+    if (kind != 4 || blockIdx.y == 0) partial[(long long)blockIdx.x * PARTIAL_STRIDE + dst] = a;
   }
 }
 
-// one CTA of 32 warps: warp w folds fields w and w + 32 of the per-CTA partials (lanes stride over the partials, then the
-// same shuffle tree) into the 74-double row
-template <int PASS>
+// one CTA of 32 warps: warp w folds fields w, w + 32, w + 64 of the per-CTA partials (lanes stride over the partials, then the
+// same shuffle tree); then 18 threads form the 74-double row from the totals and the shift
 __global__ void __launch_bounds__(1024)
-finish_kernel(const double* __restrict__ partial, int n_part, long long N, double* __restrict__ row) {
-  __shared__ double tot[3 * NS + 1];
+finish_kernel(const double* __restrict__ partial, int n_part, const double* __restrict__ x, long long ld, long long N,
+              const int* __restrict__ status, double* __restrict__ row) {
+  __shared__ double tot[4 * NS + 1];
+  __shared__ long long j0_sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nfield = PASS == 1 ? 3 * NS + 1 : NS;
-  for (int f = warp; f < nfield; f += 32) {
-    const bool is_min = PASS == 1 && f >= NS && f < 2 * NS, is_max = PASS == 1 && f >= 2 * NS && f < 3 * NS;
+  if (warp == 0) {
+    const long long j0 = N > 0 ? shift_aircraft(status, N) : 0;
+    if (lane == 0) j0_sh = j0;
+  }
+  for (int f = warp; f < 4 * NS + 1; f += 32) {
+    const bool is_min = f >= 2 * NS && f < 3 * NS, is_max = f >= 3 * NS && f < 4 * NS;
     double a = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
     for (int b = lane; b < n_part; b += 32) {
-      const double v = partial[(long long)b * 56 + f];
+      const double v = partial[(long long)b * PARTIAL_STRIDE + f];
       a = is_min ? fmin(a, v) : is_max ? fmax(a, v) : a + v;
     }
     a = is_min ? warp_min(a) : is_max ? warp_max(a) : warp_sum(a);
@@ -123,32 +137,39 @@ finish_kernel(const double* __restrict__ partial, int n_part, long long N, doubl
   }
   __syncthreads();
   const int f = threadIdx.x;
-  if (PASS == 1) {
-    if (f == 0) {
-      row[0] = (double)N;
-      row[1] = tot[3 * NS];
-    }
-    if (f < NS) row[38 + f] = tot[3 * NS] > 0.0 ? tot[f] / tot[3 * NS] : 0.0;  // mean = sum / alive
-    if (f >= NS && f < 3 * NS) row[2 + (f - NS)] = tot[f];                       // min -> row[2..19], max -> row[20..37]
-  } else if (f < NS) {
-    row[56 + f] = tot[f];
+  if (f == 0) {
+    row[0] = (double)N;
+    row[1] = tot[4 * NS];
+  }
+  if (f < NS) {
+    const double n = tot[4 * NS];
+    const double v0 = N > 0 ? x[f * ld + j0_sh] : 0.0;
+    const double c = fabs(v0) < INFINITY ? v0 : 0.0;
+    const double s1 = tot[f], s2 = tot[NS + f];
+    const double inv = n > 0.0 ? 1.0 / n : 0.0;
+    double m2 = fma(-s1, s1 * inv, s2);
+    m2 = m2 > 0.0 ? m2 : (m2 == m2 ? 0.0 : m2);  // rounding may leave a negative ulp; a NaN stays a NaN
+    row[2 + f] = tot[2 * NS + f];
+    row[20 + f] = tot[3 * NS + f];
+    row[38 + f] = n > 0.0 ? c + s1 * inv : 0.0;
+    row[56 + f] = n > 0.0 ? m2 : 0.0;
   }
 }
 
-// row: 74 doubles on the device; scratch: at least 56 * grid doubles on the device
+// row: 74 doubles on the device; scratch: at least PARTIAL_STRIDE * grid doubles on the device
 cudaError_t launch_summary(const LaunchCfg& cfg, const double* x, long long ld, long long N, const int* status, double* row,
                            double* scratch, int grid) {
-  partial_kernel<1><<<dim3(grid, 2), THREADS, 0, cfg.stream>>>(x, ld, N, status, nullptr, scratch);
-  finish_kernel<1><<<1, 1024, 0, cfg.stream>>>(scratch, grid, N, row);
-  partial_kernel<2><<<dim3(grid, 2), THREADS, 0, cfg.stream>>>(x, ld, N, status, row, scratch);
-  finish_kernel<2><<<1, 1024, 0, cfg.stream>>>(scratch, grid, N, row);
-  if (cfg.launch_counter) *cfg.launch_counter += 4;
+  // six states per CTA, two CTAs (512 threads, 116 registers, no spills) per SM: measured best of {2, 3, 6} groups x {2, 3, 4}
+  // CTAs per SM -- 0.265 ms = 4.8 TB/s at 2^23 aircraft; the three-CTA build spills its accumulators (0.298 ms)
+  partial_kernel<3, 2><<<dim3(grid, 3), THREADS, 0, cfg.stream>>>(x, ld, N, status, scratch);
+  finish_kernel<<<1, 1024, 0, cfg.stream>>>(scratch, grid, x, ld, N, status, row);
+  if (cfg.launch_counter) *cfg.launch_counter += 2;
   return cudaGetLastError();
 }
 
 int summary_grid(const LaunchCfg& cfg, long long N) {
-  // grid.x x 2 (state halves) CTAs of 256 threads: six resident per SM at most, nine independent loads per thread and
-  // iteration in flight; never more CTAs than there is work for
+  // grid.x x 3 (state groups) CTAs of 256 threads, two resident per SM, six independent loads per thread and iteration in
+  // flight; never more CTAs than there is work for
   long long want = (N + THREADS - 1) / THREADS;
   const long long cap = (long long)cfg.sm_count * 3;
   if (want > cap) want = cap;

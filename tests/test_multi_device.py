@@ -118,3 +118,41 @@ def test_slices_over_device_contexts_equal_one_context(f16):
         f16.shutdown()
         f16.init()
         f16.lib.f16_set_math_mode(prev_math)
+
+
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_survivor_compaction_equals_one_launch(f16, math):
+    """A Monte-Carlo run with casualties: xcg 0.35 open loop, +-5 % about trim, 5 s -- a third of the batch leaves the envelope.
+    With f16_set_step_compaction(1) the run is eight chunks of steps with the survivors repacked in between; states, status
+    words and step counts must be the bits of the single launch, with and without per-aircraft xcg / steps_done arrays, through
+    the host entry point (chunk pipeline) and the device entry point."""
+    g = load_golden("xcg35")
+    n, K = 140_001, 5000 if math == "fast" else 4096
+    x, u = perturbed_trim(n, g["x_trim"], seed=11, frac=0.05)
+    xcg = np.full(n, 0.35)
+    prev_math = f16.lib.f16_set_math_mode(f16.MATH_FAST if math == "fast" else f16.MATH_STRICT)
+    prev = f16.lib.f16_set_step_compaction(0)
+    try:
+        ref = f16.F16Batch(x, u, xcg=0.35)
+        ref.step(K=K)
+        dead = (ref.status != 0).mean()
+        assert 0.1 < dead < 0.9, dead          # the run does lose aircraft, and keeps some
+        f16.lib.f16_set_step_compaction(1)
+        for xc in (0.35, xcg):
+            fb = f16.F16Batch(x, u, xcg=xc)
+            fb.step(K=K)
+            assert np.array_equal(fb.x, ref.x, equal_nan=True)
+            assert np.array_equal(fb.status, ref.status) and np.array_equal(fb.steps_done, ref.steps_done)
+        # device entry point, no steps_done array
+        L = f16.lib
+        d_x, d_u, d_st = L.f16_dev_alloc(x.nbytes), L.f16_dev_alloc(u.nbytes), L.f16_dev_alloc(4 * n)
+        assert L.f16_memcpy_h2d(d_x, x.ctypes.data, x.nbytes) == 0 and L.f16_memcpy_h2d(d_u, u.ctypes.data, u.nbytes) == 0
+        assert L.step_batch_dev(d_x, n, d_u, n, n, K, 0.001, None, None, 1, None, 0.35, d_st, None) == 0
+        xo, so = np.empty_like(x), np.zeros(n, np.int32)
+        assert L.f16_memcpy_d2h(xo.ctypes.data, d_x, x.nbytes) == 0 and L.f16_memcpy_d2h(so.ctypes.data, d_st, 4 * n) == 0
+        for p in (d_x, d_u, d_st):
+            L.f16_dev_free(p)
+        assert np.array_equal(xo, ref.x, equal_nan=True) and np.array_equal(so, ref.status)
+    finally:
+        f16.lib.f16_set_step_compaction(prev)
+        f16.lib.f16_set_math_mode(prev_math)

@@ -7,7 +7,7 @@ roofline that bounds it:
   step_batch_dev K=1                        HBM: 320 B per aircraft
   linearise_batch_dev                       FP64 (17.2 k / 32.3 k flop per Jacobian pair) and HBM (3168 B written)
   trim_batch_dev                            objective evaluations/s
-  state_summary_batch_dev                   HBM: 2 x 144 B per aircraft (two passes; the second mostly from L2 when it fits)
+  state_summary_batch_dev                   HBM: 152 B per aircraft (one pass: 18 planes + the status words per group of six states)
 
 Usage: python tools/bench_entry_points.py [--math strict|fast] [--sizes 4096,65536,1048576] [--reps 5] [--staging 0|1]
 """
@@ -104,7 +104,7 @@ def main():
         if not only or "summary" in only:
             row = np.empty(74)
             b, a = timed(lambda: ck(L.state_summary_batch_dev(d_x, n, n, None, row.ctypes.data), "summary"))
-            report("state_summary_batch_dev (two passes + 592 B D2H)", b, a, nbytes=n * 2 * 144, units=n, unit_name="aircraft_per_s")
+            report("state_summary_batch_dev (one pass + 592 B D2H)", b, a, nbytes=n * 152, units=n, unit_name="aircraft_per_s")
         if (not only or "linearise" in only) and n <= (1 << 18):
             d_A, d_B = L.f16_dev_alloc(n * 324 * 8), L.f16_dev_alloc(n * 72 * 8)
             for scheme, nm, fl in ((0, "forward", 17200.0), (1, "central", 32300.0)):
