@@ -56,6 +56,7 @@ def _load():
     L.f16_use_device.argtypes = [ctypes.c_int]
     L.f16_set_host_pipeline.argtypes = [ctypes.c_int]
     L.f16_set_step_compaction.argtypes = [ctypes.c_int]
+    L.f16_set_trim_fixed_point_exit.argtypes = [ctypes.c_int]
     L.f16_shutdown.restype = None
     L.f16_last_error.restype = ctypes.c_char_p
     L.f16_set_default_xcg.argtypes = [ctypes.c_double]

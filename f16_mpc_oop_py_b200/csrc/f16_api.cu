@@ -95,6 +95,7 @@ struct State {
   int lin_variant = 0;
   bool step_chunking = true;
   bool host_pipeline = true;   // chunked H2D / kernel / D2H overlap in the host-buffer entry points
+  bool trim_fp_exit = true;    // trim_batch: fixed-point exit of the Nelder-Mead search (same results, see f16_model.cuh)
   bool compaction = false;     // long runs: survivors repacked between chunks of steps (step_compacting); opt-in
   std::atomic<double> default_xcg{0.25};
   std::atomic<int> last_status{0};
@@ -261,6 +262,7 @@ f16::LaunchCfg cfg(bool smem_tables) {
   c.step_chunking = G.step_chunking;
   c.step_progress = (int*)D->b_prog.p;
   c.step_progress_cap = (long long)(D->b_prog.cap / 4);
+  c.trim_fixed_point_exit = G.trim_fp_exit;
   return c;
 }
 f16::DevTables tabs() { return f16::DevTables{D->d_hifi, D->d_lofi, D->d_hifi_fast, 0}; }
@@ -627,6 +629,13 @@ int f16_set_step_chunking(int on) {
   std::lock_guard<std::mutex> lk(G_mu);
   int prev = G.step_chunking ? 1 : 0;
   G.step_chunking = on != 0;
+  return prev;
+}
+
+int f16_set_trim_fixed_point_exit(int on) {
+  std::lock_guard<std::mutex> lk(G_mu);
+  int prev = G.trim_fp_exit ? 1 : 0;
+  G.trim_fp_exit = on != 0;
   return prev;
 }
 

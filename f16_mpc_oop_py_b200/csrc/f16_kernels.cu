@@ -516,6 +516,7 @@ linearise_warp_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x
 #define F16_TRIM_THREADS 256
 struct TrimGuess {
   double ux[5];
+  int fixed_point_exit;
 };
 
 template <int FI, bool SMEM>
@@ -534,7 +535,7 @@ trim_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ h_g, const 
 #pragma unroll
       for (int k = 0; k < 5; k++) ux[k] = guess.ux[k];
       const TrimPoint t = trim_point(h_g[n], v_g[n]);
-      r = nelder_mead_trim<FI>(img, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux);
+      r = nelder_mead_trim<FI>(img, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux, guess.fixed_point_exit != 0);
       trim_state(t, ux, x);  // env.py:275-288: the optimiser's (unclipped) point
     } else {
       r.cost = qnan(); r.iterations = 0; r.fcalls = 0; r.converged = 0; r.status = ST_FIDELITY;
@@ -736,6 +737,7 @@ cudaError_t launch_trim(const LaunchCfg& cfg, const DevTables& tabs, const Batch
   if (N <= 0) return cudaSuccess;
   TrimGuess g;
   for (int k = 0; k < 5; k++) g.ux[k] = ux0[k];
+  g.fixed_point_exit = cfg.trim_fixed_point_exit ? 1 : 0;
   cudaError_t e = cudaSuccess;
   const bool s = cfg.smem_tables;
 #if defined(F16_FAST)

@@ -32,6 +32,7 @@ struct LaunchCfg {
   bool step_chunking = false;
   int* step_progress = nullptr;
   long long step_progress_cap = 0;
+  bool trim_fixed_point_exit = true;  // Nelder-Mead: leave a search that has reached a bitwise fixed point (f16_model.cuh)
 };
 
 #define F16_DECLARE_LAUNCHERS                                                                                        \

@@ -211,6 +211,7 @@ struct TrimCostFast {
 
 struct TrimGuessFast {
   double ux[5];
+  int fixed_point_exit;
 };
 
 template <int FI>
@@ -243,7 +244,7 @@ trim_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ h_g, c
 #pragma unroll
       for (int k = 0; k < 5; k++) ux[k] = guess.ux[k];
       const TrimPoint t = trim_point(h_g[n], v_g[n]);
-      r = nelder_mead_trim_with(cost, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux);
+      r = nelder_mead_trim_with(cost, t, sel.xcg ? sel.xcg[n] : sel.xcg_default, tol, maxiter, ux, guess.fixed_point_exit != 0);
       trim_state(t, ux, x);  // env.py:275-288: the optimiser's (unclipped) point
     } else {
       r.cost = qnan(); r.iterations = 0; r.fcalls = 0; r.converged = 0; r.status = ST_FIDELITY;
@@ -268,6 +269,7 @@ cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const 
   if (N <= 0) return cudaSuccess;
   TrimGuessFast g;
   for (int k = 0; k < 5; k++) g.ux[k] = ux0[k];
+  g.fixed_point_exit = cfg.trim_fixed_point_exit ? 1 : 0;
   if (FI)
     return launch_persistent(cfg, trim_fast_kernel<1>, 256, FAST_SMEM_BYTES, N, 256, tabs, sel, h, v, N, tol, maxiter, g, x_trim,
                              ld_x, info, ld_info, status);

@@ -134,6 +134,12 @@ int f16_set_step_compaction(int on);    /* 1: a long uniform-fidelity run (K >= 
                                           and the stopped aircraft retired to the caller's arrays.  Same bits as one launch.  Measured at 2^20
                                           aircraft x 10^4 steps: xcg 0.35 open loop (57 % of the batch lost) 369 -> 291 ms; a run that loses
                                           nobody pays for the extra launches (+0.5 %).  0 (default): one launch.  $F16_STEP_COMPACTION. */
+int f16_set_trim_fixed_point_exit(int on); /* 1 (default): trim_batch leaves a Nelder-Mead search whose shrink step moves no vertex any more (the
+                                             simplex has collapsed onto neighbouring floating-point numbers without meeting xatol /
+                                             fatol: a kink of the cost at a clipped control).  Every further iteration would repeat
+                                             the last one bit for bit, so the result at maxiter is known: same point, info = maxiter
+                                             iterations and the evaluations they would have made.  Results identical to 0 (spin to
+                                             maxiter like scipy, env.py:273); the cfg-4 grid at xcg 0.25 takes 36 ms instead of 537. */
 int f16_set_linearise_variant(int variant); /* linearise_batch kernel.  0 (default): in F16_MATH_STRICT the staged strict kernel (CTA per
                                                32 aircraft, columns over warps), in F16_MATH_FAST the two-aircraft-per-warp kernel on
                                                the fast arithmetic; 1 = strict, warp per aircraft, column per lane; 2 = strict, CTA

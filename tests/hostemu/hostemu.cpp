@@ -170,17 +170,22 @@ __attribute__((visibility("default"))) unsigned emu_calc_xdot_col(const double* 
   return st;
 }
 // trim (Nelder-Mead on the device arithmetic): x_trim[18], info = {cost, iterations, fcalls, converged}
-__attribute__((visibility("default"))) unsigned emu_trim(double h, double V, int fi, double xcg, double tol, int maxiter,
-                                                         double* x_trim, double* info) {
+// fixed_point_exit: leave a search that has reached a bitwise fixed point (1, the library's default) or spin to maxiter (0)
+__attribute__((visibility("default"))) unsigned emu_trim_fp(double h, double V, int fi, double xcg, double tol, int maxiter,
+                                                            int fixed_point_exit, double* x_trim, double* info) {
   double ux[5] = {5000, -0.09, 8.49, -0.01, 0.01};
   const f16::TrimPoint t = f16::trim_point(h, V);
-  const f16::TrimResult r = fi ? f16::nelder_mead_trim<1>(g_hifi.data(), t, xcg, tol, maxiter, ux)
-                               : f16::nelder_mead_trim<0>(g_lofi.data(), t, xcg, tol, maxiter, ux);
+  const f16::TrimResult r = fi ? f16::nelder_mead_trim<1>(g_hifi.data(), t, xcg, tol, maxiter, ux, fixed_point_exit != 0)
+                               : f16::nelder_mead_trim<0>(g_lofi.data(), t, xcg, tol, maxiter, ux, fixed_point_exit != 0);
   double x[18];
   f16::trim_state(t, ux, x);
   for (int i = 0; i < 18; i++) x_trim[i] = x[i];
   info[0] = r.cost; info[1] = r.iterations; info[2] = r.fcalls; info[3] = r.converged;
   return r.status;
+}
+__attribute__((visibility("default"))) unsigned emu_trim(double h, double V, int fi, double xcg, double tol, int maxiter,
+                                                         double* x_trim, double* info) {
+  return emu_trim_fp(h, V, fi, xcg, tol, maxiter, 1, x_trim, info);
 }
 // div_by (exact division through a rounded reciprocal) on n numerators: out[i] = the device arithmetic's a[i] / y
 __attribute__((visibility("default"))) void emu_div_by(const double* a, long long n, double y, double* out) {

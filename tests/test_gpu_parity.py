@@ -921,6 +921,27 @@ def test_bench_workload_final_state_sample_against_the_oracle(f16, oracle, mode,
     assert np.array_equal(fb.steps_done[idx][alive], np.full(int(alive.sum()), K))
 
 
+def test_trim_fixed_point_exit_is_exact_on_the_cfg4_grid(f16, mode):
+    """the 64 x 64 cfg-4 grid at xcg 0.25 (2 % of it never converges): with and without the fixed-point exit of the search the
+    same points, costs, iteration and evaluation counts, bit for bit -- and the exit is what makes the grid a 40 ms launch"""
+    import time
+    hh, vv = np.meshgrid(np.linspace(5000, 40000, 64), np.linspace(300, 900, 64), indexing="ij")
+    out = {}
+    for on in (1, 0):
+        prev = f16.lib.f16_set_trim_fixed_point_exit(on)
+        try:
+            t0 = time.perf_counter()
+            out[on] = f16.trim(hh.ravel(), vv.ravel(), xcg=0.25, maxiter=6000) + (time.perf_counter() - t0,)
+        finally:
+            f16.lib.f16_set_trim_fixed_point_exit(prev)
+    (xa, oa, ta), (xb, ob, tb) = out[1], out[0]
+    assert np.array_equal(xa, xb, equal_nan=True)
+    for k in ("fun", "nit", "nfev", "success", "status"):
+        assert np.array_equal(oa[k], ob[k], equal_nan=True), k
+    assert 0 < (~oa["success"]).sum() < 200 and (oa["nit"][~oa["success"]] == 6000).all()
+    assert ta < tb
+
+
 def test_trim_edges(f16):
     x, opt = f16.trim(np.zeros(0), np.zeros(0))
     assert x.shape == (18, 0)

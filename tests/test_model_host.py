@@ -333,6 +333,27 @@ def test_trim_nelder_mead_bit_equal(emu, oracle):
     assert np.array_equal(x, xr) and int(info[1]) == 40 == ir["iterations"] and not ir["converged"]
 
 
+def test_trim_fixed_point_exit_changes_nothing(emu, oracle):
+    """Flight conditions of the cfg-4 grid at xcg 0.25 whose search never meets xatol / fatol (the simplex collapses onto
+    neighbouring floating-point numbers at a kink of the cost, and scipy spins to maxiter -- env.py:273 asks for 50 000).  The
+    device search leaves such a fixed point early; point, cost, iteration and evaluation counts must be what the full loop
+    gives: the host compile without the exit, and the oracle's restatement of scipy's loop."""
+    emu.emu_trim_fp.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                ctypes.c_int, dp, dp]
+    stuck = 0
+    hs, vs = np.linspace(5000, 40000, 64), np.linspace(300, 900, 64)   # the cfg-4 grid
+    for h, V in ((hs[0], vs[5]), (hs[28], vs[0]), (hs[32], vs[0]), (hs[20], vs[4]), (10000.0, 700.0)):
+        xa, ia, xb, ib = np.zeros(18), np.zeros(4), np.zeros(18), np.zeros(4)
+        sa = emu.emu_trim_fp(h, V, 1, 0.25, 1e-10, 6000, 1, _p(xa), _p(ia))
+        sb = emu.emu_trim_fp(h, V, 1, 0.25, 1e-10, 6000, 0, _p(xb), _p(ib))
+        assert sa == sb and np.array_equal(xa, xb) and np.array_equal(ia, ib), (h, V, ia, ib)
+        xr, ir, sr = oracle.trim(h, V, 1, 0.25, maxiter=6000)
+        assert sa == sr and np.array_equal(xa, xr)
+        assert (ia[0], int(ia[1]), int(ia[2]), bool(ia[3])) == (ir["cost"], ir["iterations"], ir["fcalls"], ir["converged"])
+        stuck += int(ia[1]) == 6000 and not ia[3] and ia[2] > 5 * ia[1]   # a shrink (7 evaluations) every iteration
+    assert stuck == 3   # three points spin at a fixed point, one is still creeping along at the cap, 10000 ft / 700 ft/s converges
+
+
 def test_fast_calc_xdot_on_the_envelope_corners(emu_fast, oracle):
     """the extreme cells of every table axis and of the tfac^4.14 table: exactly on alpha = -20 / 45 deg, beta = +-30 deg,
     dele = +-25 deg, h = 0 / 100000 ft (cell search by rounding must land in the last cell, not beyond it), and within
