@@ -41,6 +41,7 @@ struct K_t {
   double r2d, inv15, c5_3, c7_3, tlapse, inv21_5, inv30, ninv25, half_cbar, g, S_m, inv_m, lef_q, inv_pi,
       c1_38, c1_45, c20_2, inv0_136, ixx_qr, ixx_pq, ixx_l, ixx_n, iyy_pr, iyy_p2, inv_Jy, izz_n, izz_l, izz_pq, izz_qr,
       xcg_arm;
+  double c0_2, c0_04, c0_01, c0_35;  // literals whose low word is not zero: an FP64 instruction cannot carry them as immediates
 };
 // inertia terms of nlplant.c:413-436 pre-divided by (Jx Jz - Jxz^2) resp. Jy
 #define F16_JX 9496.0
@@ -64,7 +65,8 @@ F16_KCONST K_t K = {
     (F16_JZ - F16_JX) / F16_JY, -F16_JXZ / F16_JY, 1.0 / F16_JY,
     F16_JX / F16_JD, F16_JXZ / F16_JD, (F16_JX * (F16_JX - F16_JY) + F16_JXZ * F16_JXZ) / F16_JD,
     -F16_JXZ * (F16_JX - F16_JY + F16_JZ) / F16_JD,
-    11.32 / 30.0};
+    11.32 / 30.0,
+    0.2, 0.04, 0.01, 0.35};
 
 F16_FD int lo32(double v) {
 #if defined(__CUDA_ARCH__)
@@ -218,12 +220,12 @@ F16_FD int cell_of(double u, int n_cells, double& lam) {
 // upper cell where the reference has lam = 1 - 1e-16 in the lower one) -- the same value to the last bit or two.
 F16_FD void locate_hifi(double alpha, double beta, double el, int& ia, int& ib, int& i1, int& i2, double& la, double& lb,
                         double& l1, double& l2) {
-  ia = cell_of(fma(alpha, 0.2, 4.0), 13, la);
+  ia = cell_of(fma(alpha, K.c0_2, 4.0), 13, la);
   const bool b_out = (beta < -10.0) | (beta >= 10.0);
-  ib = cell_of(fma(beta, b_out ? 0.2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
+  ib = cell_of(fma(beta, b_out ? K.c0_2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
   const bool e_out = (el < -10.0) | (el >= 10.0);
   i1 = cell_of(fma(el, e_out ? K.inv15 : 0.1, el < -10.0 ? K.c5_3 : (el >= 10.0 ? K.c7_3 : 2.0)), 4, l1);
-  i2 = cell_of(fma(el, 0.04, 1.0), 2, l2);
+  i2 = cell_of(fma(el, K.c0_04, 1.0), 2, l2);
 }
 
 // value of table `slot` of an (f, d) node at alpha weight la
@@ -249,6 +251,29 @@ F16_FD bool step_ok(const double (&x)[18]) {
   ok &= (x[12] >= 1000.0) & (x[12] <= 19000.0);
   ok &= (fabs(x[13]) <= 25.0) & (fabs(x[14]) <= 21.5) & (fabs(x[15]) <= 30.0);
   ok &= (x[16] >= 0.0) & (x[16] <= 25.0);
+  ok &= !either_nan(x[0], x[1]) & !either_nan(x[17], x[17]);
+  if (LIBM_TRIG) ok &= !either_nan(x[3], x[4]) & !either_nan(x[5], x[5]);
+  else ok &= small_angle(x[3]) & small_angle(x[4]) & small_angle(x[5]);
+  return ok;
+}
+
+// The same question asked on the integer pipe (an FP64 compare occupies the FP64 pipe like a multiply-add and yields no flop):
+// a screen on the HIGH WORDS that says "certainly inside" or "look again".  For a bound B whose low word is zero (every bound of
+// parameters.py:122-123 is such a number) |v| < B <=> hi(|v|) < hi(B), and lo <= v < hi for 0 <= lo <=> hi(v) - hi(lo) < hi(hi) -
+// hi(lo) as unsigned numbers.  A state ON a bound (or in its last 2^-20 relative), -0.0, an infinity and a NaN all fail the
+// screen; the caller then asks step_ok(), which is exact.  true implies step_ok() for the bounded states; the three unbounded
+// ones keep their NaN test and the Euler angles their small_angle().
+F16_FD bool below_abs(double v, unsigned hi_bound) { return (unsigned)(hi32(v) & 0x7fffffff) < hi_bound; }
+F16_FD bool in_range_pos(double v, unsigned hi_lo, unsigned hi_hi) { return (unsigned)hi32(v) - hi_lo < hi_hi - hi_lo; }
+template <bool LIBM_TRIG>
+F16_FD bool step_screen(const double (&x)[18]) {
+  bool ok = in_range_pos(x[2], 0u, 0x40F86A00u);                                  // 0 .. 100000
+  ok &= in_range_pos(x[6], 0u, 0x408C2000u);                                      // 0 .. 900
+  ok &= below_abs(x[7], 0x40340000u);                                             // inside -20 .. 90: |alpha| < 20
+  ok &= below_abs(x[8], 0x403E0000u) & below_abs(x[9], 0x4072C000u) & below_abs(x[10], 0x40590000u) & below_abs(x[11], 0x40490000u);
+  ok &= in_range_pos(x[12], 0x408F4000u, 0x40D28E00u);                            // 1000 .. 19000
+  ok &= below_abs(x[13], 0x40390000u) & below_abs(x[14], 0x40358000u) & below_abs(x[15], 0x403E0000u);
+  ok &= in_range_pos(x[16], 0u, 0x40390000u);                                     // 0 .. 25
   ok &= !either_nan(x[0], x[1]) & !either_nan(x[17], x[17]);
   if (LIBM_TRIG) ok &= !either_nan(x[3], x[4]) & !either_nan(x[5], x[5]);
   else ok &= small_angle(x[3]) & small_angle(x[4]) & small_angle(x[5]);
@@ -388,7 +413,7 @@ F16_FD void nlplant_extra_rows(double v6, double vt, double sa, double ca, doubl
 template <bool LIBM_TRIG, bool NLP = false, bool AUX = false>
 F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18],
                            double* aux = nullptr) {
-  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
+  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = K.c0_35;
 
   const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
   // hifi_envelope(): the elevator range is already guaranteed by the |x[13]| <= 25 bound
@@ -419,7 +444,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   }
 
   double vt = x[6];
-  if (vt <= 0.01) vt = 0.01;  // nlplant.c:104
+  if (vt <= K.c0_01) vt = K.c0_01;  // nlplant.c:104
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
 
   // atmos, nlplant.c:467-490: only qbar (Nlplant) and qbar/ps (upd_lef, utils.py:291-296) are consumed here
@@ -635,7 +660,7 @@ F16_FD double lrow(const double* row, const LofiA& A) {
 template <bool LIBM_TRIG, bool NLP = false, bool AUX = false>
 F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const double (&uc)[4], double xcg, double (&xd)[18],
                            double* aux = nullptr) {
-  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = 0.35;
+  const double B = 30.0, S = 300.0, cbar = 11.32, xcgr = K.c0_35;
   const double alpha = x[7] * K.r2d, beta = x[8] * K.r2d, el = x[13];
   if (!(fabs(beta) <= 30.0)) return false;  // lofi_envelope(): dmomdcon indexes past its arrays beyond 30 deg
 
@@ -662,7 +687,7 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   }
 
   double vt = x[6];
-  if (vt <= 0.01) vt = 0.01;  // nlplant.c:104
+  if (vt <= K.c0_01) vt = K.c0_01;  // nlplant.c:104
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
   const double tfac = fma(K.tlapse, x[2], 1.0);
   const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
@@ -810,7 +835,11 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
 #pragma unroll 1
 #endif
   for (; k < K; k++) {
-    if (!step_ok<LIBM_TRIG>(x)) break;  // env.py:117 -- the reference exit()s here; we freeze this aircraft
+    // env.py:117 -- the reference exit()s here; we freeze this aircraft.  Integer screen first, the exact comparison only for a
+    // state the screen is not sure about
+    if (!step_screen<LIBM_TRIG>(x)) {
+      if (!step_ok<LIBM_TRIG>(x)) break;
+    }
     double xd[18];
     if (LQR) {
       double u[4];
