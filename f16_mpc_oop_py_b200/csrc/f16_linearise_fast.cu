@@ -4,8 +4,8 @@
 //
 // The strict kernel (f16_kernels.cu: CTA = 32 aircraft x 8 warps, stages of f shared between columns through shared
 // memory, three barriers and a 101 KB transposing tile per group) is bound by latency: 252 registers -> 8 warps per SM, FP64
-// pipe 31 % busy.  A full evaluation on the fast arithmetic is ~640 instructions in 168 registers, which makes a barrier-
-// free mapping affordable:
+// pipe 31 % busy.  A full evaluation on the fast arithmetic is ~640 instructions, which makes a barrier-free mapping
+// affordable:
 //
 //   * a warp-task is TWO aircraft; the 16 lanes of a half-warp are the 15 perturbation columns that need Nlplant (states
 //     2..16: h, phi, theta, psi, V, alpha, beta, p, q, r, T, dh, da, dr, lf2) plus the unperturbed point.  Every lane runs the
@@ -30,7 +30,17 @@
 namespace f16 {
 namespace fast {
 
-constexpr int LF_THREADS = 384;
+// CTA size.  Measured at 2^20 points (tools/exp_lin_threads.sh), central / forward A,B pairs per second:
+//   384 threads, 168 registers (12 warps per SM): 5.4e8 / 7.6e8 -- the build spills a packed predicate mask and a state word, and
+//       with 220 KB of shared memory in use there are 8 KB of L1 left: every reload came from L2 and 5 % of all warp samples
+//       sat on one of them (ncu, stall_long_sb on the instruction after LDL);
+//   320 / 288 threads: ptxas stays at 168 registers and spills all the same: 5.1e8 / 8.1e8, 4.6e8 / 7.3e8;
+//   256 threads, 255 registers, no spills (8 warps per SM): 5.9e8 / 9.0e8  <- this one
+//   224 / 192 threads: 5.0e8 / 7.8e8, 4.3e8 / 6.7e8 (too few warps).
+#ifndef F16_LF_THREADS
+#define F16_LF_THREADS 256
+#endif
+constexpr int LF_THREADS = F16_LF_THREADS;
 constexpr int LF_IN_LD = 24;  // 18 states + 4 inputs (+ 2 pad) per staged aircraft
 
 template <int FI>
