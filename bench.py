@@ -37,11 +37,11 @@ FLOP_PER_STEP = {"open": 750.0, "lqr": 815.0}   # algorithmic FP64 flop per hifi
 BYTES_PER_AIRCRAFT_LAUNCH = 320.0               # read 18 + 4, write 18 doubles, independent of K
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default workload (2^20 aircraft,
 # K = 10000), from the committed `ncu --set full` capture profiles/r02_step_hifi_fast_chunked_k10000_ncu_summary.md:
-# 2.991 GB read + 2.423 GB written.  The time-chunked schedule (f16_step_fast.cu) passes the state through global memory
+# 3.017 GB read + 2.430 GB written.  The time-chunked schedule (f16_step_fast.cu) passes the state through global memory
 # between its 16 chunks of 625 steps: 16 x (320 B x 2^20 + status and progress words) = 5.4 GB algorithmic for THIS schedule,
 # against 335.5 MB for the unchunked kernel (whose capture, r01, showed 302 MB) -- 0.19 % of the DRAM peak over the 352 ms
 # launch either way; the chunking buys the 3 % grid tail.  Reported only when the run is that workload.
-NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 2_990_819_000 + 2_423_162_000}
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 3_017_189_000 + 2_429_674_000}
 
 # trim of the reference at 10000 ft / 700 ft/s, xcg 0.25, hifi (tests/golden/env_xcg25.npz, env.py:198-292)
 GOLDEN = os.path.join(REPO, "tests", "golden")
