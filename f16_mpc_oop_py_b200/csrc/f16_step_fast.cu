@@ -537,6 +537,90 @@ xdot_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorM
                           tiles, lane);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// step_batch with FEW steps per call (K < 8: the reference's own driving pattern, one env.step per controller update).  Such a
+// launch is HBM-bound like the one-shot kernels -- 324 B per aircraft and call against K x 690 instructions --, so it gets
+// their memory side: warp-tasks of 32 aircraft in warp-major order, the 18 + 4 input plane runs of a task as two TMA tensor
+// boxes, the boxes of the warp's next task in flight during the arithmetic and the stores of the current one.  The arithmetic
+// is step_aircraft() itself (bounds, envelope, exact status word, libm fall-back for huge Euler angles), so the results are
+// the bits of step_hifi_fast_kernel.  Measured at 2^20 aircraft, K = 1: 77 -> 66 us.
+// ------------------------------------------------------------------------------------------------------
+template <int FI, bool LQR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+step_tiled_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_u,
+                       double* __restrict__ x_g, long long ld_x, long long N, int K, double dt, int* __restrict__ status,
+                       int* __restrict__ steps_done, const __grid_constant__ fastmath::LqrDense c_lqr_fast) {
+  using S = XfSmem<FI, false, THREADS>;
+  constexpr int XF_WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* img = reinterpret_cast<const double*>(f16_smem);
+  double* buf = reinterpret_cast<double*>(f16_smem + S::IMG_PAD) + warp * S::BUF_DOUBLES;
+  const uint32_t bar_tab = smem_u32(f16_smem + S::BARS), bar_w = bar_tab + 8 * (1 + warp), buf_a = smem_u32(buf);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= XF_WARPS; i++) mbar_init(bar_tab + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // table image: global -> shared, completes on bar_tab (chunks in a per-CTA rotation, as in xdot_fast_kernel)
+    mbar_expect_tx(bar_tab, S::IMG_BYTES);
+    if (FI) {
+      constexpr int CHUNK = XF_TABLE_CHUNK, NCHUNK = (S::IMG_BYTES + CHUNK - 1) / CHUNK;
+      int c = (int)(blockIdx.x % NCHUNK);
+#pragma unroll 1
+      for (int k = 0; k < NCHUNK; k++) {
+        const int off = c * CHUNK;
+        bulk_g2s(smem_u32(f16_smem + off), reinterpret_cast<const char*>(tabs.hifi_fast) + off,
+                 (S::IMG_BYTES - off) < CHUNK ? (S::IMG_BYTES - off) : CHUNK, bar_tab);
+        c = c + 1 == NCHUNK ? 0 : c + 1;
+      }
+    } else {
+      bulk_g2s(smem_u32(f16_smem), tabs.lofi, F16_IMG_LOFI_BYTES, bar_tab);
+      bulk_g2s(smem_u32(f16_smem + F16_IMG_LOFI_BYTES), tabs.hifi_fast + F16_FI_POW, 2 * F16_FI_NPOW * 8, bar_tab);
+    }
+  }
+  const long long tiles = (N + 31) >> 5;
+  const long long stride = (long long)XF_WARPS * gridDim.x;
+  long long t = (long long)warp * gridDim.x + blockIdx.x;
+  auto issue = [&](long long tile) {  // the whole warp, converged
+    if (tile >= tiles) return;
+    if (lane == 0) {
+      const int col = (int)(tile << 5);
+      mbar_expect_tx(bar_w, 22 * 256);
+      tma_box_g2s(buf_a, &map_x, col, bar_w);
+      tma_box_g2s(buf_a + 18 * 256, &map_u, col, bar_w);
+    }
+  };
+  issue(t);
+  mbar_wait(bar_tab, 0);
+  uint32_t phase = 0;
+  for (; t < tiles; t += stride) {
+    const long long n = (t << 5) + lane;
+    double x[18], u_in[4];
+    mbar_wait(bar_w, phase);
+    phase ^= 1;
+#pragma unroll
+    for (int i = 0; i < 18; i++) x[i] = buf[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u_in[i] = buf[(18 + i) * 32 + lane];
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the reads above before the next task's bulk copies
+    issue(t + stride);
+    const int own = n < N ? owns<FI>(sel, n) : 0;
+    if (own == 1) {
+      const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+      int k;
+      const unsigned st = fastmath::step_aircraft<LQR, FI, 0>(img, x, u_in, LQR ? &c_lqr_fast : nullptr, xcg, dt, K, k);
+#pragma unroll
+      for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
+      if (status) status[n] = (int)st;
+      if (steps_done) steps_done[n] = k;
+    } else if (own < 0) {  // a fidelity flag that is neither 0 nor 1: reported by the hifi launch
+      if (status) status[n] = (int)ST_FIDELITY;
+      if (steps_done) steps_done[n] = 0;
+    }
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -639,6 +723,25 @@ cudaError_t launch_fast_probe(const LaunchCfg& cfg, const DevTables& tabs, const
   return cudaGetLastError();
 }
 
+// the short-step launch: true when it was taken (K < 8, a batch worth staging tables for, arrays a tensor map can describe)
+template <int FI>
+static bool launch_step_tiled(const LaunchCfg& cfg, const DevTables& tabs, const BatchSel& sel, double* x, long long ld_x, const double* u,
+                              long long ld_u, long long N, int K, double dt, const LqrLaw* lqr_host, const fastmath::LqrDense& dense,
+                              int* status, int* steps_done, cudaError_t* err) {
+  static const bool off = getenv("F16_STEP_TILED") && atoi(getenv("F16_STEP_TILED")) == 0;
+  if (off || !cfg.smem_tables || K < 1 || K >= 8 || N < 4096) return false;
+  CUtensorMap mx, mu;
+  memset(&mx, 0, sizeof mx);
+  memset(&mu, 0, sizeof mu);
+  if (!soa_tensor_map(&mx, x, ld_x, N, 18) || !soa_tensor_map(&mu, u, ld_u, N, 4)) return false;
+  constexpr int T = 256;
+  *err = lqr_host ? launch_persistent(cfg, step_tiled_fast_kernel<FI, true, T>, T, XfSmem<FI, false, T>::TOTAL, N, T, tabs, sel, mx, mu, x,
+                                      ld_x, N, K, dt, status, steps_done, dense)
+                  : launch_persistent(cfg, step_tiled_fast_kernel<FI, false, T>, T, XfSmem<FI, false, T>::TOTAL, N, T, tabs, sel, mx, mu, x,
+                                      ld_x, N, K, dt, status, steps_done, dense);
+  return true;
+}
+
 using StepKern = void (*)(DevTables, BatchSel, double*, long long, const double*, long long, long long, int, double, int*,
                           int*, const fastmath::LqrDense);
 
@@ -660,6 +763,8 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   fastmath::LqrDense dense = fastmath::LqrDense();
   if (lqr_host) fastmath::make_dense_law(*lqr_host, dense);
   const bool mpc_cols = lqr_host && dense.colmask == F16_LQR_MPC_COLMASK;  // the reference's own column set: compile-time columns
+  cudaError_t te = cudaSuccess;
+  if (launch_step_tiled<1>(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, dense, status, steps_done, &te)) return te;
   int threads = cfg.step_threads;
   // time-chunked scheduling (no grid tail): the default CTA size, a uniform hifi batch, enough steps to cut into chunks and
   // more than one round of warp-tasks; needs the status words (they carry "stopped" between chunks) and the progress flags
@@ -701,6 +806,8 @@ cudaError_t launch_step_lofi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   if (N <= 0) return cudaSuccess;
   fastmath::LqrDense dense = fastmath::LqrDense();
   if (lqr_host) fastmath::make_dense_law(*lqr_host, dense);
+  cudaError_t te = cudaSuccess;
+  if (launch_step_tiled<0>(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, dense, status, steps_done, &te)) return te;
   const int smem = F16_LOFI_STEP_IMG_DOUBLES * 8;
   StepKern k = !lqr_host ? step_lofi_fast_kernel<false, 384>
                : dense.colmask == F16_LQR_MPC_COLMASK ? step_lofi_fast_kernel<true, 384, F16_LQR_MPC_COLMASK>

@@ -478,6 +478,37 @@ def test_step_time_chunked_schedule_equals_the_plain_kernel(f16, with_law):
         f16.lib.f16_set_math_mode(prev_mode)
 
 
+@pytest.mark.parametrize("K", [1, 3, 7])
+def test_short_step_tiled_kernel_equals_the_plain_kernel(f16, K):
+    """step_batch with K < 8 on >= 4096 aircraft takes the TMA-tiled short-step kernel (f16_step_fast.cu::step_tiled_fast_kernel);
+    the same aircraft inside a batch of 4095 take the plain step kernel.  Same bits -- hifi, lofi, a mixed batch with
+    per-aircraft xcg, open and closed loop, a ragged batch size, aircraft outside the envelope among them."""
+    prev = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        g = load_golden("xcg35")
+        n, m = 70_001, 4095
+        x, u = perturbed_trim(n, g["x_trim"], seed=21, frac=0.05)
+        x[7, 5::97] = 1.2          # alpha outside the hifi table: stopped with a status word
+        x[6, 7::101] = 950.0       # airspeed beyond its bound
+        r = np.random.default_rng(2)
+        fi_mixed = (r.uniform(size=n) < 0.6).astype(np.uint8)
+        xcg_mixed = np.where(r.uniform(size=n) < 0.5, 0.25, 0.35)
+        mpc_idx = list(g["mpc_x_idx"])
+        law = f16.make_lqr(-g["K_lqr"], mpc_idx, g["x_trim"][mpc_idx], g["u_trim"], rows=[1, 2, 3])
+        for fi, xcg in ((1, 0.35), (0, 0.25), (fi_mixed, xcg_mixed)):
+            for lqr in (None, law):
+                big = f16.F16Batch(x, u, fi_flag=fi, xcg=xcg)
+                big.step(K=K, lqr=lqr)
+                small = f16.F16Batch(x[:, :m], u[:, :m], fi_flag=fi if np.ndim(fi) == 0 else fi[:m],
+                                     xcg=xcg if np.ndim(xcg) == 0 else xcg[:m])
+                small.step(K=K, lqr=lqr)
+                assert np.array_equal(big.x[:, :m], small.x, equal_nan=True)
+                assert np.array_equal(big.status[:m], small.status) and np.array_equal(big.steps_done[:m], small.steps_done)
+                assert (big.status != 0).sum() > 100 and (big.status == 0).sum() > 60_000
+    finally:
+        f16.lib.f16_set_math_mode(prev)
+
+
 def test_step_freeze_policy(f16, oracle):
     g = load_golden("xcg35")
     x = np.repeat(g["x_trim"][:, None], 6, axis=1)
