@@ -70,6 +70,9 @@ def test_fails_loudly_without_gpu():
         pass
     with pytest.raises(f.F16Error, match="no CPU path"):
         f.init()
+    with pytest.raises(f.F16Error, match="no CPU path"):
+        f.init_devices()            # the multi-GPU form of the same call
+    assert f.lib.f16_device_count() == 0 and f.lib.f16_device() == -1 and f.lib.f16_use_device(0) < 0
     xu = np.zeros((17, 4))
     with pytest.raises(f.F16Error):
         f.nlplant(xu)
