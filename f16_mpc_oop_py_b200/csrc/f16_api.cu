@@ -473,9 +473,14 @@ int on_devices(long long N, long long min_per_device, F f) {
       }
       errs[i] = t_err;
     };
-    for (size_t i = 1; i < spans.size(); i++) workers.emplace_back(body, i);
     Dev* mine = D;
+    size_t started = 1;
+    try {
+      for (; started < spans.size(); started++) workers.emplace_back(body, started);
+    } catch (...) {  // no more threads: the calling thread takes the remaining slices one after the other
+    }
     body(0);
+    for (size_t i = started; i < spans.size(); i++) body(i);
     for (std::thread& w : workers) w.join();
     D = mine;
     cudaSetDevice(D->ordinal);
