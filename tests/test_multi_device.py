@@ -156,3 +156,113 @@ def test_survivor_compaction_equals_one_launch(f16, math):
     finally:
         f16.lib.f16_set_step_compaction(prev)
         f16.lib.f16_set_math_mode(prev_math)
+
+
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_device_entry_points_stay_inside_their_arrays(f16, math):
+    """compute-sanitizer is not available on the GPU pool: canaries instead.  Every *_dev entry point runs on arrays whose
+    planes are wider than the batch (plane stride ld > N, odd -- no tensor map, plain loads -- and even -- TMA boxes), in a
+    buffer with a guard band behind the last plane; the padding columns, the guard bands and the inputs must come back
+    bit for bit, for ragged batch sizes around the warp / CTA / chunk boundaries."""
+    L = f16.lib
+    prev_math = L.f16_set_math_mode(f16.MATH_FAST if math == "fast" else f16.MATH_STRICT)
+    prev_comp = L.f16_set_step_compaction(1)
+    CANARY = -1.2345678901234567e+300
+    g = load_golden("xcg35")
+
+    def dev(a):
+        p = L.f16_dev_alloc(a.nbytes)
+        assert p and L.f16_memcpy_h2d(p, a.ctypes.data, a.nbytes) == 0
+        return p
+
+    def back(p, like):
+        out = np.empty_like(like)
+        assert L.f16_memcpy_d2h(out.ctypes.data, p, like.nbytes) == 0
+        return out
+
+    try:
+        for n, pad, K in ((1, 3, 1), (31, 1, 2), (4097, 37, 1), (4097, 64, 7), (70_001, 64, 1), (70_001, 37, 9), (66_000, 64, 4096)):
+            ld = n + pad
+            x, u = perturbed_trim(n, g["x_trim"], seed=n, frac=0.05)
+            X = np.full((19, ld), CANARY); X[:18, :n] = x          # plane 18 = guard band
+            U = np.full((5, ld), CANARY); U[:4, :n] = u
+            O = np.full((19, ld), CANARY)
+            ST = np.full(ld + 64, 0x5A5A5A5A, dtype=np.int32)
+            KD = np.full(ld + 64, 0x5A5A5A5A, dtype=np.int32)
+            d_x, d_u, d_o, d_st, d_k = dev(X), dev(U), dev(O), dev(ST), dev(KD)
+            # calc_xdot / Nlplant: outputs in O, inputs untouched
+            assert L.calc_xdot_batch_dev(d_x, ld, d_u, ld, d_o, ld, None, 1, None, 0.35, n, d_st) == 0
+            o = back(d_o, O)
+            assert np.all(o[:18, n:] == CANARY) and np.all(o[18] == CANARY) and np.isfinite(o[:18, :n]).all()
+            assert L.Nlplant_batch_dev(d_x, ld, d_o, ld, None, 1, None, 0.35, n, d_st) == 0
+            o = back(d_o, O)
+            assert np.all(o[:18, n:] == CANARY) and np.all(o[18] == CANARY)
+            assert np.array_equal(back(d_x, X), X) and np.array_equal(back(d_u, U), U)
+            # linearise (small n only: 3 KB of output per aircraft)
+            if n <= 4097:
+                A = np.full((n + 2, 324), CANARY); B = np.full((n + 2, 72), CANARY)
+                d_a, d_b = dev(A), dev(B)
+                assert L.linearise_batch_dev(d_x, ld, d_u, ld, n, 1e-5, 1, d_a, d_b, None, 1, None, 0.35, d_st) == 0
+                a, b = back(d_a, A), back(d_b, B)
+                assert np.all(a[n:] == CANARY) and np.all(b[n:] == CANARY) and np.isfinite(a[:n]).all() and np.isfinite(b[:n]).all()
+                L.f16_dev_free(d_a); L.f16_dev_free(d_b)
+            # the step: state advanced in place, nothing else touched
+            assert L.step_batch_dev(d_x, ld, d_u, ld, n, K, 0.001, None, None, 1, None, 0.35, d_st, d_k) == 0
+            x1, st, kd = back(d_x, X), back(d_st, ST), back(d_k, KD)
+            assert np.all(x1[:18, n:] == CANARY) and np.all(x1[18] == CANARY) and np.array_equal(back(d_u, U), U)
+            assert np.all(st[n:] == 0x5A5A5A5A) and np.all(kd[n:] == 0x5A5A5A5A)
+            assert np.all((kd[:n] == K) | (st[:n] != 0)) and np.isfinite(x1[:18, :n]).all()
+            row = f16.state_summary_dev(d_x, ld, n, d_st)
+            assert row[0] == n and row[1] == (st[:n] == 0).sum()
+            for p in (d_x, d_u, d_o, d_st, d_k):
+                L.f16_dev_free(p)
+    finally:
+        L.f16_set_step_compaction(prev_comp)
+        L.f16_set_math_mode(prev_math)
+
+
+def test_host_entry_points_stay_inside_their_arrays(f16):
+    """the same for the host-buffer calls (chunk pipeline, 2-D copies into slices of the caller's planes): guard bands behind
+    every output array, a ragged batch of 300 001 aircraft = four chunks"""
+    L = f16.lib
+    prev_math = L.f16_set_math_mode(f16.MATH_FAST)
+    CANARY, GUARD = -1.2345678901234567e+300, 4096
+    try:
+        g = load_golden("xcg25")
+        n = 300_001
+        x, u = perturbed_trim(n, g["x_trim"], seed=4, frac=0.05)
+
+        def guarded(a):
+            buf = np.full(a.size + GUARD, CANARY)
+            buf[:a.size] = a.ravel()
+            return buf
+
+        def vp(a):
+            return ctypes.c_void_p(a.ctypes.data)
+
+        X, U, O = guarded(x), guarded(u), np.full(18 * n + GUARD, CANARY)
+        ST = np.full(n + GUARD, 0x5A5A5A5A, dtype=np.int32)
+        KD = np.full(n + GUARD, 0x5A5A5A5A, dtype=np.int32)
+        assert L.calc_xdot_batch(vp(X), vp(U), vp(O), None, 1, None, 0.25, n, vp(ST)) == 0
+        assert np.all(O[18 * n:] == CANARY) and np.isfinite(O[:18 * n]).all() and np.all(ST[n:] == 0x5A5A5A5A)
+        assert np.array_equal(X[:18 * n], x.ravel()) and np.all(X[18 * n:] == CANARY) and np.all(U[4 * n:] == CANARY)
+        O[:] = CANARY
+        assert L.Nlplant_batch(vp(X), vp(O), None, 1, None, 0.25, n, vp(ST)) == 0
+        assert np.all(O[18 * n:] == CANARY) and np.all(ST[n:] == 0x5A5A5A5A)
+        for K in (1, 600):
+            X = guarded(x)
+            assert L.step_batch(vp(X), vp(U), n, K, 0.001, None, None, 1, None, 0.25, vp(ST), vp(KD)) == 0
+            assert np.all(X[18 * n:] == CANARY) and np.all(U[4 * n:] == CANARY) and np.array_equal(U[:4 * n], u.ravel())
+            assert np.all(ST[n:] == 0x5A5A5A5A) and np.all(KD[n:] == 0x5A5A5A5A) and np.all(KD[:n] == K)
+        m = 40_003
+        A, B = np.full(m * 324 + GUARD, CANARY), np.full(m * 72 + GUARD, CANARY)
+        xs, us = np.ascontiguousarray(x[:, :m]), np.ascontiguousarray(u[:, :m])
+        assert L.linearise_batch(vp(xs), vp(us), m, 1e-5, 0, vp(A), vp(B), None, 1, None, 0.25, vp(ST)) == 0
+        assert np.all(A[m * 324:] == CANARY) and np.all(B[m * 72:] == CANARY) and np.isfinite(A[:m * 324]).all()
+        t = 5000
+        h, v = np.linspace(5000, 30000, t), np.linspace(400, 800, t)
+        XT, INFO = np.full(18 * t + GUARD, CANARY), np.full(4 * t + GUARD, CANARY)
+        assert L.trim_batch(vp(h), vp(v), t, 1e-10, 3000, None, vp(XT), vp(INFO), None, 1, None, 0.35, vp(ST)) == 0
+        assert np.all(XT[18 * t:] == CANARY) and np.all(INFO[4 * t:] == CANARY) and np.isfinite(XT[:18 * t]).all()
+    finally:
+        L.f16_set_math_mode(prev_math)
