@@ -266,3 +266,40 @@ def test_host_entry_points_stay_inside_their_arrays(f16):
         assert np.all(XT[18 * t:] == CANARY) and np.all(INFO[4 * t:] == CANARY) and np.isfinite(XT[:18 * t]).all()
     finally:
         L.f16_set_math_mode(prev_math)
+
+
+def test_entry_points_from_concurrent_host_threads(f16):
+    """two host threads hammer different entry points at once (ctypes releases the GIL; the library serialises on its mutex):
+    every call returns the result of the same call made alone"""
+    import threading
+    g = load_golden("xcg25")
+    x, u = perturbed_trim(50_001, g["x_trim"], seed=8, frac=0.05)
+    prev = f16.lib.f16_set_math_mode(f16.MATH_FAST)
+    try:
+        fb = f16.F16Batch(x, u, xcg=0.25)
+        ref_xd = fb._calc_xdot(x, u)
+        fb.step(K=50)
+        ref_x = fb.x.copy()
+        bad = []
+
+        def derivs():
+            b = f16.F16Batch(x, u, xcg=0.25)
+            for _ in range(15):
+                if not np.array_equal(b._calc_xdot(x, u), ref_xd):
+                    bad.append("calc_xdot")
+
+        def steps():
+            for _ in range(15):
+                b = f16.F16Batch(x, u, xcg=0.25)
+                b.step(K=50)
+                if not np.array_equal(b.x, ref_x):
+                    bad.append("step")
+
+        ts = [threading.Thread(target=derivs), threading.Thread(target=steps), threading.Thread(target=derivs)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not bad, bad
+    finally:
+        f16.lib.f16_set_math_mode(prev)
