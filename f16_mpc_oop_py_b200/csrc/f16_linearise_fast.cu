@@ -193,7 +193,7 @@ static __device__ __noinline__ void lin_redo_pass(DevTables tabs, BatchSel sel, 
 }
 
 template <int FI>
-__global__ void __maxnreg__(65536 / LF_THREADS / 8 * 8 > 255 ? 255 : 65536 / LF_THREADS / 8 * 8)
+__global__ void __launch_bounds__(LF_THREADS, 1)
 linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g,
                       long long ld_u, long long N, double eps, int scheme, double* __restrict__ A_g, double* __restrict__ B_g,
                       int* __restrict__ status, unsigned* __restrict__ redo) {

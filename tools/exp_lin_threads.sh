@@ -1,6 +1,6 @@
 #!/bin/bash
 # experiment (run under gpurun): CTA size of linearise_fast_kernel -- registers per thread against warps per SM
-for T in "256" "320" "288" "352"; do
+for T in 384 320 256 224 192; do
   rm -f f16_mpc_oop_py_b200/csrc/build/linearise_fast.o
   make -s -C f16_mpc_oop_py_b200/csrc EXTRA="-DF16_LF_THREADS=$T" > /dev/null 2>&1
   grep -A2 "linearise_fast_kernelILi1" f16_mpc_oop_py_b200/csrc/build/ptxas_linearise_fast.log | grep -E "spill|Used" | tr '\n' ' '; echo
