@@ -55,6 +55,8 @@ def _load():
     L.f16_init_devices.argtypes = [ctypes.c_char_p, c_ip, ctypes.c_int]
     L.f16_use_device.argtypes = [ctypes.c_int]
     L.f16_set_host_pipeline.argtypes = [ctypes.c_int]
+    L.f16_plan_slices.argtypes = [c_ll, c_ll, ctypes.c_int, ctypes.POINTER(c_ll)]
+    L.f16_plan_chunks.argtypes = [c_ll, c_ll, ctypes.c_int, ctypes.POINTER(c_ll), c_ip]
     L.f16_set_step_compaction.argtypes = [ctypes.c_int]
     L.f16_set_trim_fixed_point_exit.argtypes = [ctypes.c_int]
     L.f16_shutdown.restype = None

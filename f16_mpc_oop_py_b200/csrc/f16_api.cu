@@ -439,8 +439,8 @@ int run_pipeline(long long n, const Chunks& ch, bool work_blocks, In in, Work wo
 struct Span {
   long long lo, n;
 };
-std::vector<Span> device_spans(long long N, long long min_per_device) {
-  long long parts = (long long)G.devs.size();
+std::vector<Span> device_spans(long long N, long long min_per_device, long long contexts = -1) {
+  long long parts = contexts > 0 ? contexts : (long long)G.devs.size();
   if (min_per_device > 0 && N / min_per_device < parts) parts = N / min_per_device;
   if (parts < 1) parts = 1;
   std::vector<Span> v;
@@ -549,6 +549,29 @@ void f16_shutdown(void) {
   G.cur = 0;
   G.payload.clear();
   G.table_source.clear();
+}
+
+// host logic only (no CUDA call): how a host-buffer batch call would cut N aircraft over `contexts` device contexts and, on one
+// context, into pipeline chunks.  lo_n [2 * contexts] = (first aircraft, count) per slice; returns the number of slices used.
+int f16_plan_slices(long long N, long long min_per_device, int contexts, long long* lo_n) {
+  if (N < 0 || contexts < 1 || contexts > 64 || !lo_n) return F16_ERR_ARG;
+  try {
+    const std::vector<Span> v = N > 0 ? device_spans(N, min_per_device, contexts) : std::vector<Span>();
+    for (size_t i = 0; i < v.size(); i++) {
+      lo_n[2 * i] = v[i].lo;
+      lo_n[2 * i + 1] = v[i].n;
+    }
+    return (int)v.size();
+  } catch (const std::exception&) {
+    return F16_ERR_HOST;
+  }
+}
+int f16_plan_chunks(long long n, long long min_chunk, int max_chunks, long long* chunk, int* slots) {
+  if (n < 1 || min_chunk < 1 || max_chunks < 1 || !chunk || !slots) return F16_ERR_ARG;
+  const Chunks c = plan_chunks(n, min_chunk, max_chunks);
+  *chunk = c.chunk;
+  *slots = c.slots;
+  return c.count;
 }
 
 int f16_device_count(void) {

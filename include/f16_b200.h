@@ -113,6 +113,11 @@ int f16_init_devices(const char *table_path, const int *devices, int ndev);
 int f16_device_count(void);      /* number of contexts; 0 before init */
 int f16_use_device(int index);   /* context (index into the f16_init_devices list) of the *_dev entry points, the memory helpers
                                     and the timers; returns the previous index or an F16_ERR_* code */
+/* The host logic behind the two calls above, without a GPU (used by the CPU tests): the slices a batch of N aircraft is cut into
+ * over `contexts` device contexts (lo_n [2 * contexts] = first aircraft and count of each; returns the number of slices), and the
+ * pipeline chunks of one slice (returns their number; *chunk = aircraft per chunk, *slots = device slots in use). */
+int f16_plan_slices(long long N, long long min_per_device, int contexts, long long *lo_n);
+int f16_plan_chunks(long long n, long long min_chunk, int max_chunks, long long *chunk, int *slots);
 int f16_set_host_pipeline(int on); /* 1 (default): the host-buffer batch calls run as a chunk pipeline on each device (H2D of chunk
                                       c + 1 and D2H of chunk c - 1 under the kernels of chunk c); 0: one chunk.  Same bits. */
 void f16_shutdown(void);

@@ -83,3 +83,29 @@ def test_two_rank_gloo_split_and_statistics():
         np.testing.assert_allclose(m["var"], x[:, alive].var(axis=1), rtol=1e-12)
         np.testing.assert_array_equal(m["min"], x[:, alive].min(axis=1))
         np.testing.assert_array_equal(m["max"], x[:, alive].max(axis=1))
+
+
+def test_library_slices_and_chunks_cover_the_batch():
+    """the in-library multi-GPU split (f16_init_devices) and the chunk pipeline, host logic only: slices are contiguous, start
+    on multiples of 32 aircraft (a warp-task never straddles two devices), cover [0, N) and are balanced to within one warp-task;
+    a batch too small to feed every device uses fewer; chunks are multiples of 32 and at most three slots are in use"""
+    import ctypes
+    import f16_mpc_oop_py_b200 as f16
+    L = f16.lib
+    for n, mpd, ctx in ((1 << 20, 16384, 8), (300_001, 16384, 8), (70_001, 16384, 8), (5, 16384, 8), (64 << 20, 16384, 8),
+                        (4096 * 3 + 17, 4096, 4), (1, 1, 64), (2_000_000_011, 16384, 3)):
+        out = (ctypes.c_longlong * (2 * ctx))()
+        k = L.f16_plan_slices(n, mpd, ctx, out)
+        assert 1 <= k <= ctx and k == max(1, min(ctx, n // mpd))
+        lo = [out[2 * i] for i in range(k)]
+        cnt = [out[2 * i + 1] for i in range(k)]
+        assert lo[0] == 0 and all(l % 32 == 0 for l in lo) and all(c > 0 for c in cnt)
+        assert all(lo[i] + cnt[i] == lo[i + 1] for i in range(k - 1)) and lo[-1] + cnt[-1] == n
+        assert max(cnt) - min(cnt) <= 32 + 31
+    assert L.f16_plan_slices(0, 16384, 8, (ctypes.c_longlong * 16)()) == 0
+    assert L.f16_plan_slices(10, 1, 0, (ctypes.c_longlong * 2)()) == -3
+    for n, mc, mx in ((1 << 20, 1 << 18, 4), (1 << 20, 1 << 16, 8), (300_001, 1 << 16, 8), (100, 1 << 16, 8), (1 << 27, 1 << 18, 4)):
+        chunk, slots = ctypes.c_longlong(0), ctypes.c_int(0)
+        c = L.f16_plan_chunks(n, mc, mx, ctypes.byref(chunk), ctypes.byref(slots))
+        assert 1 <= c <= mx and chunk.value % 32 == 0 and slots.value == min(c, 3)
+        assert (c - 1) * chunk.value < n <= c * chunk.value and (c == 1 or chunk.value >= mc)
