@@ -63,6 +63,23 @@ def test_legacy_nlplant_and_atmos(f16, oracle, golden):
     f16.lib.f16_set_default_xcg(0.25)
 
 
+def test_atmosphere_over_the_whole_altitude_range(f16, oracle, mode):
+    """atmos_batch against the oracle's atmos (the reference's pow(tfac, 4.14), C/nlplant.c:467-490) from -10 000 to 120 000 ft:
+    the device build's table-and-series power (f16_model.cuh::pow_4_14) on every one of its 48 centres, half-way between them,
+    at both ends of its table, and the libm fall-back beyond.  mach is exact to rounding; qbar and ps carry the power: 4 ulp."""
+    c = (18.5 + np.arange(48)) / 64                                   # centres of the table, as tfac
+    tf = np.concatenate([c, c + 0.5 / 64, c - 0.5 / 64, np.nextafter(c + 0.5 / 64, 0), [0.28125, np.nextafter(1.03125, 0), 1.03125,
+                                                                                        0.2, 1.07]])
+    alt = np.concatenate([(1 - tf) / 0.703e-5, np.linspace(-10_000, 120_000, 5001), [0.0, 35000.0, np.nextafter(35000.0, 0), 1e5]])
+    vt = np.full(alt.size, 650.0)
+    vt[::7] = 0.005
+    out = f16.atmos(alt, vt)
+    ref = np.array([oracle.atmos(float(a), float(v)) for a, v in zip(alt, vt)]).T
+    # strict: reference operation order, 4 ulp for the power; F16_MATH_FAST contracts the products around it: 1e-13
+    bar = 4 * np.spacing(np.abs(ref)) if mode == "strict" else 1e-13 * np.abs(ref)
+    assert np.all(np.abs(out - ref) <= bar), float(np.max(np.abs(out - ref) / np.abs(ref)))
+
+
 def test_dropin_shim_libraries(f16, golden):
     """C/nlplant_xcg25.so and C/nlplant_xcg35.so as parameters.py:108-114 loads them"""
     xcg = float(golden["xcg"])
