@@ -144,7 +144,7 @@ static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) 
 static void sincos_libm(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 #endif
 
-// 0.5 * rho0 * tfac^4.14 for tfac in [0.28125, 1.03125): table of centres + binomial series (15 FP64 instructions)
+// 0.5 * rho0 * tfac^4.14 for tfac in [0.28125, 1.03125): table of centres + binomial series (13 FP64 instructions)
 F16_FD double half_rho(const double* img, double tfac) {
   const double magic = 6755399441055744.0;
   const double u = fma(tfac, 64.0, -18.5);
@@ -154,9 +154,7 @@ F16_FD double half_rho(const double* img, double tfac) {
   i = i < 0 ? 0 : (i > F16_FI_NPOW - 1 ? F16_FI_NPOW - 1 : i);
   const d2 e = ld2(img + F16_FI_POW + 2 * i);
   const double s = d * e.x;  // (tfac - c_i) / c_i
-  double p = fma(s, K.PW[8], K.PW[7]);
-  p = fma(s, p, K.PW[6]);
-  p = fma(s, p, K.PW[5]);
+  double p = fma(s, K.PW[6], K.PW[5]);  // degree 7: the terms left out are C(4.14, 8) s^8 <= 1.4e-16 and C(4.14, 9) s^9 <= 2e-18
   p = fma(s, p, K.PW[4]);
   p = fma(s, p, K.PW[3]);
   p = fma(s, p, K.PW[2]);
@@ -181,51 +179,47 @@ F16_FD double rcp_nr(double v) {
 #endif
 }
 
-// cell and weight on a piecewise-uniform axis.  u = position in cell units (cell k spans [k, k+1], n cells).
-// k = floor(u) as the round-to-nearest of (u - 0.5) + 1.5*2^52 (low word of the sum; no conversion instruction, no
-// breakpoint load), clamped to [0, n-1] on the integer pipe BEFORE the weight is formed, and the weight is the exact
-// difference lam = u - k (k rebuilt as a double from the clamped low word).  What this gives (mexndinterp.c:97-143):
-//   * u strictly inside a cell -> that cell, 0 < lam < 1: the reference's (j, j+1) and its lambda;
-//   * u == k (a breakpoint; u - 0.5 is a tie, rounded to even) -> cell k with lam = 0 or cell k-1 with lam = 1, both of
-//     which evaluate to the node value f_k like the reference's exact hit (j, j) -- fma(1, d, f) = f + (f_k - f) up to
-//     the rounding of the stored difference;
-//   * the ends of the axis: u == n -> cell n-1, lam = 1; the affine map to cell units may round the bottom to -2e-16
-//     (fma(-20, 0.2, 4)) -> cell 0, lam = -2e-16.
-// There is no margin: a query a relative 1e-16 above a breakpoint is in the upper cell.  (Round 1 shrank u by 2^-30
-// first, which put a 2^-30-wide band above every breakpoint into the LOWER cell with lam = 1 + delta, an extrapolation
-// with error delta * (slope change): 9e-9 scaled at alpha = 30 deg + 1.5e-8.)
-F16_FD double magic_plus(int k) {  // 1.5*2^52 + k for 0 <= k < 2^31: k is the low word
+// Cell and weight of a query on the four hifi axes (ALPHA -20:5:45; BETA1 -30:5:-10:2:10:5:30; DH1 -25,-10,0,10,25; DH2 -25,0,25
+// -- check_grids() verifies the grids are these).  Every breakpoint is a whole number of degrees, so the cell of a query follows
+// from the integer t = floor(query - axis start), and that integer is exact: it is the low word of ONE addition rounded towards
+// minus infinity, query + (1.5 * 2^52 - axis start) (no product, no conversion instruction, no comparison on the FP64 pipe).
+// alpha: cell = t / 5 (a multiply and a shift); beta: a 61-byte table in the image; elevator: three integer compares.  The weight
+// is one fma, lam = fma(query, 1 / cell width, -lower breakpoint / cell width), both constants from the image (F16_FI_AX).
+// What this gives (mexndinterp.c:97-143):
+//   * the cell is the reference's (j, j+1) for every query strictly inside a cell, with its lambda to an ulp or two;
+//   * a query ON breakpoint j is in cell j with lam = 0 up to the rounding of 1 / width (|lam| <= 5e-16), which evaluates to the
+//     node value f_j like the reference's exact hit (j, j); at the top of an axis the cell is the last one and lam = 1;
+//   * there is no margin anywhere: a query a relative 1e-16 above a breakpoint is in the upper cell, one below it in the lower.
+// (Round 1 found the cell by rounding a scaled query shrunk by 2^-30, which put a 2^-30-wide band above every breakpoint into the
+// LOWER cell with lam = 1 + delta, an extrapolation with error delta * (slope change): 9e-9 scaled at alpha = 30 deg + 1.5e-8.
+// Until this version the position in cell units was formed first and rounded, five FP64 instructions per axis plus the
+// comparisons that pick the piece of a piecewise-uniform axis; now two.)
+F16_FD int floor_plus(double v, int shift) {  // floor(v) + shift for |v| < 2^31 - shift
 #if defined(__CUDA_ARCH__)
-  return __hiloint2double(0x43380000, k);
+  return __double2loint(__dadd_rd(v, 6755399441055744.0 + shift));  // 1.5 * 2^52 + shift: an ulp is 1 up there
 #else
-  unsigned long long b = 0x4338000000000000ULL | (unsigned)k;
-  double v;
-  __builtin_memcpy(&v, &b, 8);
-  return v;
+  return (int)floor(v) + shift;
 #endif
 }
-F16_FD int cell_of(double u, int n_cells, double& lam) {
-  const double magic = 6755399441055744.0;
-  const double tm = (u - 0.5) + magic;
-  int k = lo32(tm);
-  k = k < 0 ? 0 : (k > n_cells - 1 ? n_cells - 1 : k);
-  lam = u - (magic_plus(k) - magic);
-  return k;
-}
+F16_FD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// the four cells of a hifi look-up (ALPHA -20:5:45; BETA1 -30:5:-10:2:10:5:30; DH1 -25,-10,0,10,25; DH2 -25,0,25 --
-// check_grids() verifies the grids are these).  beta and DH1 are piecewise uniform: two compares pick scale and offset of
-// the affine map to cell units.  Position on the axis in cell units is ONE fma of the query, so it carries the rounding of
-// that fma (<= 2^-53 * 18 in cell units): a query within that distance of a breakpoint may be placed ON it (lam = 0 in the
-// upper cell where the reference has lam = 1 - 1e-16 in the lower one) -- the same value to the last bit or two.
-F16_FD void locate_hifi(double alpha, double beta, double el, int& ia, int& ib, int& i1, int& i2, double& la, double& lb,
-                        double& l1, double& l2) {
-  ia = cell_of(fma(alpha, K.c0_2, 4.0), 13, la);
-  const bool b_out = (beta < -10.0) | (beta >= 10.0);
-  ib = cell_of(fma(beta, b_out ? K.c0_2 : 0.5, beta < -10.0 ? 6.0 : (beta >= 10.0 ? 12.0 : 9.0)), 18, lb);
-  const bool e_out = (el < -10.0) | (el >= 10.0);
-  i1 = cell_of(fma(el, e_out ? K.inv15 : 0.1, el < -10.0 ? K.c5_3 : (el >= 10.0 ? K.c7_3 : 2.0)), 4, l1);
-  i2 = cell_of(fma(el, K.c0_04, 1.0), 2, l2);
+// ia, i1, i2: cells on ALPHA, DH1, DH2; ib: cell on BETA1.  The clamps only matter for a query outside an axis (the callers
+// exclude it): they keep the table reads inside the image.
+F16_FD void locate_hifi(const double* img, double alpha, double beta, double el, int& ia, int& ib, int& i1, int& i2, double& la,
+                        double& lb, double& l1, double& l2) {
+  const double* ax = img + F16_FI_AX;
+  ia = clampi((floor_plus(alpha, 20) * 13108) >> 16, 0, F16_FI_NAC - 1);  // t / 5 for 0 <= t <= 65; alpha = 45 is in the last cell
+  la = fma(alpha, K.c0_2, ax[F16_AX_A + ia]);
+  const int tb = clampi(floor_plus(beta, 30), 0, 60);
+  ib = reinterpret_cast<const unsigned char*>(ax + F16_AX_LUTB)[tb];
+  const d2 wb = ld2(ax + F16_AX_TB + 2 * tb);
+  lb = fma(beta, wb.x, wb.y);
+  const int te = floor_plus(el, 25);
+  i1 = clampi((te >= 15) + (te >= 25) + (te >= 35), 0, 3);
+  i2 = te >= 25;
+  const d2 w1 = ld2(ax + F16_AX_D1 + 2 * i1);
+  l1 = fma(el, w1.x, w1.y);
+  l2 = fma(el, K.c0_04, i2 ? 0.0 : 1.0);
 }
 
 // value of table `slot` of an (f, d) node at alpha weight la
@@ -265,6 +259,19 @@ F16_FD bool step_ok(const double (&x)[18]) {
 // ones keep their NaN test and the Euler angles their small_angle().
 F16_FD bool below_abs(double v, unsigned hi_bound) { return (unsigned)(hi32(v) & 0x7fffffff) < hi_bound; }
 F16_FD bool in_range_pos(double v, unsigned hi_lo, unsigned hi_hi) { return (unsigned)hi32(v) - hi_lo < hi_hi - hi_lo; }
+// Two more comparisons of calc_xdot_* moved off the FP64 pipe; both are exact for every value that is not a NaN (the callers'
+// preconditions exclude a NaN altitude or airspeed): doubles order like their bit patterns read as signed integers as long as one
+// side is positive, and 35000.0 has a zero low word.
+F16_FD bool at_or_above_35000(double alt) { return hi32(alt) >= 0x40E11700; }  // nlplant.c:475
+F16_FD bool at_most_0_01(double v) {                                           // nlplant.c:104
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(v) <= 0x3F847AE147AE147BLL;
+#else
+  long long b;
+  __builtin_memcpy(&b, &v, 8);
+  return b <= 0x3F847AE147AE147BLL;
+#endif
+}
 template <bool LIBM_TRIG>
 F16_FD bool step_screen(const double (&x)[18]) {
   bool ok = in_range_pos(x[2], 0u, 0x40F86A00u);                                  // 0 .. 100000
@@ -371,7 +378,10 @@ F16_FD void actuator_rows(const double (&x)[18], const double (&uc)[4], double a
   xd[15] = r15;
   xd[16] = r16;
   // rate limits (utils.py:299-330) only cost selects when one of them is active (or a value is NaN)
-  if (!((fabs(r12) <= 10000.0) & (fabs(r13) <= 60.0) & (fabs(r14) <= 80.0) & (fabs(r15) <= 120.0) & (fabs(r16) <= 25.0))) {
+  // asked on the integer pipe like step_screen(): |r| < B <=> hi(|r|) < hi(B) for a bound whose low word is zero; a rate ON its
+  // limit, beyond it or NaN takes the exact clips
+  if (!(below_abs(r12, 0x40C38800u) & below_abs(r13, 0x404E0000u) & below_abs(r14, 0x40540000u) & below_abs(r15, 0x405E0000u) &
+        below_abs(r16, 0x40390000u))) {
     xd[12] = clipd(r12, -10000, 10000);
     xd[13] = clipd(r13, -60, 60);
     xd[14] = clipd(r14, -80, 80);
@@ -421,7 +431,7 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
 
   double la, lb, l1, l2;
   int ia, ib, i1, i2;
-  locate_hifi(alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
+  locate_hifi(img, alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
 
   double sa, ca, sb, cb, st, ct, sphi, cphi, spsi, cpsi;
   sincos_quarter(x[7], sa, ca);
@@ -444,12 +454,12 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   }
 
   double vt = x[6];
-  if (vt <= K.c0_01) vt = K.c0_01;  // nlplant.c:104
+  if (at_most_0_01(vt)) vt = K.c0_01;  // nlplant.c:104
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
 
   // atmos, nlplant.c:467-490: only qbar (Nlplant) and qbar/ps (upd_lef, utils.py:291-296) are consumed here
   const double tfac = fma(K.tlapse, x[2], 1.0);
-  const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
+  const double temp = at_or_above_35000(x[2]) ? 390.0 : 519.0 * tfac;
   const double hrho = half_rho(img, tfac);
   const double qbar = hrho * (vt * vt);
   // one reciprocal for 1/(vt cb), 1/vt, 1/ct and 1/temp
@@ -585,6 +595,8 @@ F16_FD bool calc_xdot_hifi(const double* img, const double (&x)[18], const doubl
   }
   // actuators and leading-edge flap, utils.py:289-330.  qbar/ps of atmos(alt, x[6]) = 0.5 x6^2 / (1715 temp)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
+  // utils.py:292 forms x[7] * 180 / pi; x[7] * (180 / pi) is the same angle to two ulp, but a forward difference of the flap rate
+  // over eps = 1e-5 turns two ulp of a 20-degree alpha into 1.4e-8 of dA[16][7] (measured on the cfg-4 grid): keep the first product
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
   actuator_rows(x, uc, atmos_out, alpha_deg, xd);
   if (AUX) { aux[0] = atmos_out; aux[1] = alpha_deg; }
@@ -603,7 +615,7 @@ F16_FD void probe_hifi(const double* img, double alpha, double beta, double el, 
                        double (&lam)[4]) {
   double la, lb, l1, l2;
   int ia, ib, i1, i2;
-  locate_hifi(alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
+  locate_hifi(img, alpha, beta, el, ia, ib, i1, i2, la, lb, l1, l2);
   cells[0] = ia; cells[1] = ib; cells[2] = i1; cells[3] = i2;
   lam[0] = la; lam[1] = lb; lam[2] = l1; lam[3] = l2;
   for (int i = 0; i < 44; i++) o[i] = 0.0;
@@ -687,10 +699,10 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   }
 
   double vt = x[6];
-  if (vt <= K.c0_01) vt = K.c0_01;  // nlplant.c:104
+  if (at_most_0_01(vt)) vt = K.c0_01;  // nlplant.c:104
   const double P = x[9], Q = x[10], R = x[11], T = x[12];
   const double tfac = fma(K.tlapse, x[2], 1.0);
-  const double temp = (x[2] >= 35000.0) ? 390.0 : 519.0 * tfac;
+  const double temp = at_or_above_35000(x[2]) ? 390.0 : 519.0 * tfac;
   const double hrho = half_rho(img + F16_IMG_LOFI_DOUBLES - F16_FI_POW, tfac);
   const double qbar = hrho * (vt * vt);
   const double vc = vt * cb, tc = ct * temp;
@@ -818,6 +830,8 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
   }
   // actuators and leading-edge flap, utils.py:289-330 (the flap states evolve in the lofi model too; Nlplant ignores them)
   const double atmos_out = (x[6] * x[6]) * inv_temp * K.lef_q;
+  // utils.py:292 forms x[7] * 180 / pi; x[7] * (180 / pi) is the same angle to two ulp, but a forward difference of the flap rate
+  // over eps = 1e-5 turns two ulp of a 20-degree alpha into 1.4e-8 of dA[16][7] (measured on the cfg-4 grid): keep the first product
   const double alpha_deg = (x[7] * 180.0) * K.inv_pi;
   actuator_rows(x, uc, atmos_out, alpha_deg, xd);
   if (AUX) { aux[0] = atmos_out; aux[1] = alpha_deg; }
@@ -826,20 +840,22 @@ F16_FD bool calc_xdot_lofi(const double* img, const double (&x)[18], const doubl
 
 // K fused Euler steps of env.py::step from step k; stops (k < K on return) at the first state that fails step_ok or
 // leaves the tables.  The state is not advanced on the failing step.
+// The bound check of env.py:117 -- the reference exit()s there; we freeze this aircraft -- is asked about the NEW state at the
+// bottom of the loop body (integer screen first, the exact comparison only for a state the screen is not sure about): its ~40
+// integer instructions sit in the same basic block as the FP64 tail of the step that produced the state and issue in its
+// shadow, instead of forming a block of their own at the top.  The state after the last step is screened for nothing.
 template <bool LQR, bool LIBM_TRIG, int FI = 1, int COLMASK = 0>
 F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4], const LqrDense* lqr, double xcg, double dt,
                      int k, int K) {
   double uc[4];
   if (!LQR) clip_commands(u_in, uc);
+  if (k >= K) return k;
+  bool ok = step_screen<LIBM_TRIG>(x);
+  if (!ok) ok = step_ok<LIBM_TRIG>(x);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (; k < K; k++) {
-    // env.py:117 -- the reference exit()s here; we freeze this aircraft.  Integer screen first, the exact comparison only for a
-    // state the screen is not sure about
-    if (!step_screen<LIBM_TRIG>(x)) {
-      if (!step_ok<LIBM_TRIG>(x)) break;
-    }
+  while (ok) {
     double xd[18];
     if (LQR) {
       double u[4];
@@ -851,6 +867,10 @@ F16_FD int run_steps(const double* img, double (&x)[18], const double (&u_in)[4]
 #pragma unroll
 #endif
     for (int i = 0; i < 18; i++) x[i] = fma(xd[i], dt, x[i]);  // env.py:126
+    k++;
+    ok = step_screen<LIBM_TRIG>(x);
+    if (!ok) ok = step_ok<LIBM_TRIG>(x);
+    ok &= k < K;
   }
   return k;
 }

@@ -94,7 +94,14 @@ enum F16G2Slot {
 #define F16_FI_G3A_STRIDE 6
 #define F16_FI_G2 11072      // alpha x beta group: 19*13 nodes x 16 tables x (f, d) (+2 pad: node stride 272 B = 16 mod 128,
 #define F16_FI_G2_STRIDE 34    //   so that lanes in neighbouring cells do not meet in the same shared-memory banks)
-#define F16_FI_DOUBLES 19470
+// axis tables of locate_hifi(): the cell of a query is found from the INTEGER part of (query - axis start) -- every breakpoint of
+// ALPHA1 / BETA1 / DH1 / DH2 is a whole number of degrees -- and the weight is one fma(query, 1 / cell width, offset of the cell)
+#define F16_FI_AX 19470      // start of the axis tables (16-byte aligned)
+#define F16_AX_A 0           // alpha: 4 - k for cell k = 0..12 (+3 pad): la = fma(alpha, 0.2, 4 - k)
+#define F16_AX_D1 16         // DH1: (1 / width, -(lower breakpoint) / width) for cell 0..3
+#define F16_AX_LUTB 24       // BETA1: 64 bytes, cell of floor(beta + 30) = 0..60
+#define F16_AX_TB 32         // BETA1: (1 / width, -(lower breakpoint) / width) of that cell, again by floor(beta + 30): 61 x 2
+#define F16_FI_DOUBLES 19624
 #define F16_FI_BYTES (F16_FI_DOUBLES * 8)
 
 enum F16FastG1 {  // table order inside a G1 cell

@@ -297,6 +297,27 @@ void build_hifi_fast_image(const std::vector<double>& p, bool clr_from_file, std
     img[F16_FI_POW + 2 * i] = (double)(1.0L / (64.0L * c));
     img[F16_FI_POW + 2 * i + 1] = (double)(0.5L * 2.377e-3L * powl(c, (long double)4.14));
   }
+  // axis tables of fastmath::locate_hifi (check_grids() has verified that every breakpoint is a whole number of degrees)
+  {
+    double* ax = &img[F16_FI_AX];
+    const double* A = &p[F16_CANON_A1];
+    const double* B = &p[F16_CANON_B];
+    const double* D1 = &p[F16_CANON_D1];
+    for (int k = 0; k < F16_FI_NAC; k++) ax[F16_AX_A + k] = -A[k] / (A[k + 1] - A[k]);  // 4 - k
+    for (int k = 0; k < F16_N_D1 - 1; k++) {
+      ax[F16_AX_D1 + 2 * k] = 1.0 / (D1[k + 1] - D1[k]);
+      ax[F16_AX_D1 + 2 * k + 1] = -D1[k] / (D1[k + 1] - D1[k]);
+    }
+    unsigned char lut[64] = {0};
+    for (int t = 0; t <= 60; t++) {  // beta in [B[0] + t, B[0] + t + 1)
+      int k = 0;
+      while (k < F16_N_B - 2 && B[0] + t >= B[k + 1]) k++;
+      lut[t] = (unsigned char)k;
+      ax[F16_AX_TB + 2 * t] = 1.0 / (B[k + 1] - B[k]);
+      ax[F16_AX_TB + 2 * t + 1] = -B[k] / (B[k + 1] - B[k]);
+    }
+    memcpy(ax + F16_AX_LUTB, lut, 64);
+  }
   const int g1_src[FG1_COUNT][2] = {
       {FT_CXq, 20}, {FT_dCXq_lef, 14}, {FT_CZq, 20}, {FT_CMq, 20}, {FT_dCMq_lef, 14}, {FT_dCm, 20}, {FT_CYr, 20},
       {FT_dCYr_lef, 14}, {FT_CYp, 20}, {FT_dCYp_lef, 14}, {FT_CNr, 20}, {FT_dCNr_lef, 14}, {FT_CNp, 20}, {FT_dCNp_lef, 14},
