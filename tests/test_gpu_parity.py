@@ -1183,6 +1183,31 @@ def test_calc_xdot_in_the_breakpoint_bands(f16, oracle, mode, xcg):
     assert scaled_err(out, ref) < TOL_DERIV
 
 
+def test_integer_pipe_comparisons_on_their_thresholds(f16, oracle, mode):
+    """The comparisons that f16_fast.cuh asks on the integer pipe -- airspeed floor (nlplant.c:104), tropopause (nlplant.c:475), the
+    five actuator rate limits (utils.py:299-330) -- ON, one ulp either side of and well either side of their thresholds: the
+    derivative of the step kernel (dt = 1) and of the one-shot kernel against the reference .so, both builds."""
+    from _inputs import comparison_threshold_cases
+    x, u = comparison_threshold_cases(X_TRIM_XCG25, oracle.atmos)
+    ref, rst = oracle.calc_xdot_batch(x, u, 1, 0.25, checker(oracle))
+    assert not rst.any()
+    for row, lim in ((12, 10000.0), (13, 60.0), (14, 80.0), (15, 120.0), (16, 25.0)):
+        assert (np.abs(ref[row]) == lim).any() and (np.abs(ref[row]) < lim).any(), row
+    fb = f16.F16Batch(x, u, xcg=0.25)
+    out = fb._calc_xdot(x, u)
+    assert not fb.last_status.any()
+    assert scaled_err(out, ref) < TOL_DERIV
+    # the step kernel: an airspeed of 0 is ON a state bound (exact path of the screen) and steps like any other
+    err = _dt1_derivative_error(f16, oracle, x, u, 0.25)
+    assert err.max() < TOL_DERIV, (err.max(), np.unravel_index(np.argmax(err), err.shape))
+    # and in a batch large enough for the TMA-tiled kernels (the same states, repeated)
+    reps = 4096 // x.shape[1] + 1
+    xb, ub = np.ascontiguousarray(np.tile(x, (1, reps))), np.ascontiguousarray(np.tile(u, (1, reps)))
+    fb = f16.F16Batch(xb, ub, xcg=0.25)
+    outb = fb._calc_xdot(xb, ub)
+    assert scaled_err(outb, np.tile(ref, (1, reps))) < TOL_DERIV
+
+
 # ---------------------------------------------------------------------------------------------------------
 # end-of-run statistics reduced on the device (f16_stats.cu; SURVEY 8e / 8f rank 4)
 # ---------------------------------------------------------------------------------------------------------

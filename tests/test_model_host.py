@@ -469,3 +469,22 @@ def test_fast_image_and_cell_search_against_the_reference_accessors(emu_fast, or
     # s["on_node_other_cell"]: queries on or an ulp from a breakpoint that the one-FMA map to cell units places 1e-16 to
     # its other side (check_fast_probe bounds their weight to 4 ulp of 0 / 1): the same value to rounding, never a band
     print(s)
+
+
+def test_fast_integer_comparisons_on_their_thresholds(emu_fast, oracle):
+    """the comparisons that f16_fast.cuh asks on the integer pipe (airspeed floor, tropopause, the five actuator rate limits) ON,
+    one ulp either side of and well either side of their thresholds: same derivative as the reference to 1e-12"""
+    from _inputs import X_TRIM_XCG25, comparison_threshold_cases
+    from conftest import scaled_err
+    X, U = comparison_threshold_cases(X_TRIM_XCG25, oracle.atmos)
+    ref, st = oracle.calc_xdot_batch(X, U, 1, 0.25, PORT)
+    assert not st.any() and X.shape[1] > 60
+    out = np.empty_like(ref)
+    for i in range(X.shape[1]):
+        xd = np.zeros(18)
+        assert emu_fast.emu_calc_xdot_fast(_p(np.ascontiguousarray(X[:, i])), _p(np.ascontiguousarray(U[:, i])), _p(xd), 0.25) == 0
+        out[:, i] = xd
+    # every rate limit is met from both sides somewhere in the set
+    for row, lim in ((12, 10000.0), (13, 60.0), (14, 80.0), (15, 120.0), (16, 25.0)):
+        assert (np.abs(ref[row]) == lim).any() and (np.abs(ref[row]) < lim).any(), row
+    assert scaled_err(out, ref) < 1e-12
