@@ -332,28 +332,33 @@ static inline void make_dense_law(const LqrLaw& l, LqrDense& d) {
   }
 }
 
-// COLMASK != 0: the set of gain columns is known at compile time (the reference's own law: its nine MPC states,
-// parameters.py:135) -- no branch per column, so the column updates interleave; 0: read it from the law.
-#define F16_LQR_MPC_COLMASK 0x30F98  // states 3, 4, 7, 8, 9, 10, 11, 16, 17
+// COLMASK != 0: the shape of the law is known at compile time (the reference's own law: gains on its nine MPC states,
+// parameters.py:135, driving elevator, aileron and rudder; the thrust command stays the caller's) -- bits 0..17 the set of gain
+// columns, bits 20..23 the set of driven rows.  No branch per column, so the column updates interleave, and no multiply-add (nor
+// gain load) for a row that is not driven.  0: both sets are read from the law.
+#define F16_LQR_MPC_COLMASK 0x30F98                              // states 3, 4, 7, 8, 9, 10, 11, 16, 17
+#define F16_LQR_MPC_SHAPE (F16_LQR_MPC_COLMASK | (0xE << 20))    // ... driving rows 1, 2, 3
 template <int COLMASK = 0>
 F16_FD void lqr_action_dense(const LqrDense& l, const double (&x)[18], const double (&u_in)[4], double (&u)[4]) {
+  constexpr int COLS = COLMASK & 0x3FFFF, ROWS = (COLMASK >> 20) & 0xF;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < 18; i++) {
-    if (COLMASK ? ((COLMASK >> i) & 1) : ((l.colmask >> i) & 1)) {
+    if (COLS ? ((COLS >> i) & 1) : ((l.colmask >> i) & 1)) {
       const double e = x[i] - l.xr[i];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (int r = 0; r < 4; r++) acc[r] = fma(l.Kf[i][r], e, acc[r]);
+      for (int r = 0; r < 4; r++)
+        if (!ROWS || ((ROWS >> r) & 1)) acc[r] = fma(l.Kf[i][r], e, acc[r]);
     }
   }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int r = 0; r < 4; r++) u[r] = ((l.row_mask >> r) & 1) ? (l.u0[r] - acc[r]) : u_in[r];
+  for (int r = 0; r < 4; r++) u[r] = ((ROWS ? ROWS : l.row_mask) >> r) & 1 ? (l.u0[r] - acc[r]) : u_in[r];
 }
 
 // utils.py:308-330 command saturation (loop-invariant in open loop)

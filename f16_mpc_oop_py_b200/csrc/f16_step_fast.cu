@@ -762,7 +762,7 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   if (N <= 0) return cudaSuccess;
   fastmath::LqrDense dense = fastmath::LqrDense();
   if (lqr_host) fastmath::make_dense_law(*lqr_host, dense);
-  const bool mpc_cols = lqr_host && dense.colmask == F16_LQR_MPC_COLMASK;  // the reference's own column set: compile-time columns
+  const bool mpc_cols = lqr_host && dense.colmask == F16_LQR_MPC_COLMASK && dense.row_mask == 0xE;  // the reference's own law: compile-time shape
   cudaError_t te = cudaSuccess;
   if (launch_step_tiled<1>(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, dense, status, steps_done, &te)) return te;
   int threads = cfg.step_threads;
@@ -789,13 +789,13 @@ cudaError_t launch_step_hifi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
     plan.blk_rem = groups - plan.blk_lo * n_blk;
     plan.big_items = (plan.blk_lo + 1) * C * plan.blk_rem;
     ChunkKern ck = !lqr_host ? step_hifi_fast_chunked_kernel<false, 0>
-                   : mpc_cols ? step_hifi_fast_chunked_kernel<true, F16_LQR_MPC_COLMASK>
+                   : mpc_cols ? step_hifi_fast_chunked_kernel<true, F16_LQR_MPC_SHAPE>
                               : step_hifi_fast_chunked_kernel<true, 0>;
     return launch_persistent(cfg, ck, 384, FAST_SMEM_BYTES, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, chunk, dt, status, steps_done,
                              cfg.step_progress, plan, dense);
   }
   StepKern k = lqr_host ? pick_step_hifi_fast<true>(cfg.smem_tables, threads) : pick_step_hifi_fast<false>(cfg.smem_tables, threads);
-  if (mpc_cols && cfg.smem_tables && threads == 384) k = step_hifi_fast_kernel<true, true, 384, F16_LQR_MPC_COLMASK>;
+  if (mpc_cols && cfg.smem_tables && threads == 384) k = step_hifi_fast_kernel<true, true, 384, F16_LQR_MPC_SHAPE>;
   const int smem = cfg.smem_tables ? FAST_SMEM_BYTES : 0;
   return launch_persistent(cfg, k, threads, smem, N, threads, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done, dense);
 }
@@ -810,7 +810,7 @@ cudaError_t launch_step_lofi_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   if (launch_step_tiled<0>(cfg, tabs, sel, x, ld_x, u, ld_u, N, K, dt, lqr_host, dense, status, steps_done, &te)) return te;
   const int smem = F16_LOFI_STEP_IMG_DOUBLES * 8;
   StepKern k = !lqr_host ? step_lofi_fast_kernel<false, 384>
-               : dense.colmask == F16_LQR_MPC_COLMASK ? step_lofi_fast_kernel<true, 384, F16_LQR_MPC_COLMASK>
+               : (dense.colmask == F16_LQR_MPC_COLMASK && dense.row_mask == 0xE) ? step_lofi_fast_kernel<true, 384, F16_LQR_MPC_SHAPE>
                                                       : step_lofi_fast_kernel<true, 384>;
   return launch_persistent(cfg, k, 384, smem, N, 384, tabs, sel, x, ld_x, u, ld_u, N, K, dt, status, steps_done, dense);
 }
