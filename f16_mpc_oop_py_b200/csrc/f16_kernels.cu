@@ -173,12 +173,22 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
 #pragma unroll
     for (int i = 0; i < 4; i++) u_in[i] = u_g[i * ld_u + n];
     const double xcg = sel.xcg ? sel.xcg[n] : sel.xcg_default;
+    // env.py:117 -- the reference exit()s on a state outside its bounds; we freeze this aircraft.  The check is an integer
+    // screen (bounds_screen) with step_bounds() behind it for a state the screen is not sure about, and it is asked about the
+    // NEW state at the bottom of the loop body, where its integer instructions issue in the shadow of the step's FP64 tail
+    // (same scheme as fastmath::run_steps; same bits as checking every state with step_bounds at the top).
     unsigned st = 0;
     int k = 0;
+    bool go = false;
+    if (K > 0) {
+      go = !(either_nan(u_in[0], u_in[1]) || either_nan(u_in[2], u_in[3])) && bounds_screen(x);
+      if (!go) {
+        st = step_bounds(x, u_in);
+        go = st == 0;
+      }
+    }
 #pragma unroll 1
-    for (; k < K; k++) {
-      st = step_bounds(x, u_in);  // env.py:117 -- the reference exit()s here; we freeze this aircraft
-      if (st) break;
+    while (go) {
       double u[4], xd[18];
       if (LQR) {
         lqr_action(c_lqr, x, u_in, u);
@@ -190,6 +200,13 @@ step_kernel(DevTables tabs, BatchSel sel, double* __restrict__ x_g, long long ld
       if (st) break;
 #pragma unroll
       for (int i = 0; i < 18; i++) x[i] = x[i] + xd[i] * dt;  // env.py:126
+      k++;
+      go = bounds_screen(x);
+      if (!go & (k < K)) {
+        st = step_bounds(x, u_in);
+        go = st == 0;
+      }
+      go &= k < K;
     }
 #pragma unroll
     for (int i = 0; i < 18; i++) x_g[i * ld_x + n] = x[i];
