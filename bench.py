@@ -36,12 +36,13 @@ sys.path.insert(0, REPO)
 FLOP_PER_STEP = {"open": 750.0, "lqr": 815.0}   # algorithmic FP64 flop per hifi aircraft-step
 BYTES_PER_AIRCRAFT_LAUNCH = 320.0               # read 18 + 4, write 18 doubles, independent of K
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default workload (2^20 aircraft,
-# K = 10000), from an ncu capture of this build (profiles/r02_step_dram_traffic.md): 201.2 MB read + 121.3 MB written against
+# K = 10000), from the ncu capture of this build (profiles/r02_step_hifi_fast_chunked_k10000_ncu_summary.md; the earlier captures
+# are in profiles/r02_step_dram_traffic.md): 197.3 MB read + 116.8 MB written against
 # 335.5 MB algorithmic (320 B x 2^20) + 4 MB of status words -- part of the state still sits in L2 from the copy that precedes
 # the launch.  The time-chunked schedule (f16_step_fast.cu) passes the state through global memory between its 16 chunks of 625
 # steps; its item order keeps a block of groups inside L2 from one chunk to the next (L2 hit rate 77 %), so that traffic never
 # reaches DRAM (the first version of the schedule moved 5.4 GB per launch).  Reported only when the run is that workload.
-NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 201_180_000 + 121_260_000}
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, "open", "fast"): 197_272_576 + 116_838_656}
 
 # trim of the reference at 10000 ft / 700 ft/s, xcg 0.25, hifi (tests/golden/env_xcg25.npz, env.py:198-292)
 GOLDEN = os.path.join(REPO, "tests", "golden")
