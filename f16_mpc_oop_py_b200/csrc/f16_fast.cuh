@@ -13,7 +13,7 @@
 //     argument reduction; phi, theta, psi use a two-constant Cody-Waite reduction; coefficients live in the
 //     constant bank (no UMOV pairs in the instruction stream);
 //   * rho = rho0 * tfac^4.14 (nlplant.c:478): tfac in [0.297, 1] on the bounded altitude range, evaluated as
-//     c^4.14 * (1+s)^4.14 with c from a 48-entry table and a degree-9 binomial series in |s| <= 0.027;
+//     c^4.14 * (1+s)^4.14 with c from a 48-entry table and a degree-7 binomial series in |s| <= 0.027;
 //   * Vt/alpha/beta dots use U = vt ca cb, V = vt sb, W = vt sa cb to cancel vt analytically; qbar/ps of the LEF
 //     schedule (utils.py:296) cancels rho.
 //
@@ -661,7 +661,7 @@ F16_FD void probe_hifi(const double* img, double alpha, double beta, double el, 
 // alpha is not confined to the hifi tables here, so it takes the reduced sincos like the Euler angles.
 // The prologue (trig, atmosphere, reciprocals, kinematics) and the epilogue (accelerations, moments, actuators) repeat
 // calc_xdot_hifi's on purpose: the hifi function is the headline kernel's loop body, and its schedule (168 registers, no
-// spills, 59 % of the FP64 peak) does not survive being cut into shared pieces -- ptxas is that sensitive here.
+// spills, 64 % of the FP64 peak) does not survive being cut into shared pieces -- ptxas is that sensitive here.
 // ------------------------------------------------------------------------------------------------------
 #define F16_LOFI_STEP_IMG_DOUBLES (F16_IMG_LOFI_DOUBLES + 2 * F16_FI_NPOW)
 

@@ -17,7 +17,7 @@ namespace fast {
 
 // ------------------------------------------------------------------------------------------------------
 // step_batch, hifi, F16_MATH_FAST: the same K fused Euler steps on the re-associated arithmetic of f16_fast.cuh
-// (fast table image: 171 KB in shared memory, one CTA per SM).  The per-step checks are the cheap "all inside"
+// (fast table image: 157 KB in shared memory, one CTA per SM).  The per-step checks are the cheap "all inside"
 // form; the exact status word is rebuilt from the frozen state when an aircraft stops.
 // ------------------------------------------------------------------------------------------------------
 constexpr int FAST_SMEM_BYTES = F16_FI_BYTES + 16;
@@ -326,7 +326,7 @@ cudaError_t launch_trim_fast(const LaunchCfg& cfg, const DevTables& tabs, const 
 //     zero-filled by the hardware, so the ragged last task needs no special case.  The boxes of the warp's NEXT task are
 //     requested as soon as the current values are in registers, so they fly during the arithmetic and the stores of the
 //     current one; the first task's boxes are requested before the CTA waits for its table image;
-//   * tables: the (f, d) image in shared memory (155 KB hifi / 7 KB lofi), one CTA of 384 threads per SM;
+//   * tables: the (f, d) image in shared memory (157 KB hifi / 7 KB lofi), one CTA of 384 threads per SM;
 //   * output: 18 coalesced 8-byte stores per lane straight from registers (a shared output tile does not fit beside the
 //     image).
 // An aircraft outside the preconditions of the fast arithmetic (a NaN anywhere, altitude outside the density table, an angle
@@ -450,7 +450,7 @@ xdot_fast_kernel(DevTables tabs, BatchSel sel, const __grid_constant__ CUtensorM
   if (threadIdx.x == 0) {  // table image: global -> shared, completes on bar_tab
     mbar_expect_tx(bar_tab, S::IMG_BYTES);
     if (FI) {
-      // every CTA of the grid reads the same 155 KB at the same moment: each starts at a different chunk, so that at any time
+      // every CTA of the grid reads the same 157 KB at the same moment: each starts at a different chunk, so that at any time
       // the requests of the 148 SMs are spread over the L2 slices instead of queueing at the few that hold "the current" chunk
       constexpr int CHUNK = XF_TABLE_CHUNK, NCHUNK = (S::IMG_BYTES + CHUNK - 1) / CHUNK;
       int c = (int)(blockIdx.x % NCHUNK);

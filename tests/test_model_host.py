@@ -356,7 +356,7 @@ def test_trim_fixed_point_exit_changes_nothing(emu, oracle):
 
 def test_fast_calc_xdot_on_the_envelope_corners(emu_fast, oracle):
     """the extreme cells of every table axis and of the tfac^4.14 table: exactly on alpha = -20 / 45 deg, beta = +-30 deg,
-    dele = +-25 deg, h = 0 / 100000 ft (cell search by rounding must land in the last cell, not beyond it), and within
+    dele = +-25 deg, h = 0 / 100000 ft (the cell search must land in the last cell, not beyond it), and within
     an ulp of interior breakpoints"""
     from _inputs import X_TRIM_XCG25
     from conftest import scaled_err
