@@ -39,7 +39,10 @@ def main():
     f16.init(device=0)
     L.f16_set_math_mode(f16.MATH_FAST if args.math == "fast" else f16.MATH_STRICT)
     L.f16_set_table_staging(args.staging)
-    peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except OSError:
+        peaks = {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     pk = ctypes.c_double(0.0)
     L.f16_measure_fp64_peak(200.0, ctypes.byref(pk))
