@@ -30,26 +30,33 @@
 namespace f16 {
 namespace fast {
 
-// CTA size.  Measured at 2^20 points (tools/exp_lin_threads.sh), central / forward A,B pairs per second:
-//   384 threads, 168 registers (12 warps per SM): 5.4e8 / 7.6e8 -- the build spills a packed predicate mask and a state word, and
-//       with 220 KB of shared memory in use there are 8 KB of L1 left: every reload came from L2 and 5 % of all warp samples
-//       sat on one of them (ncu, stall_long_sb on the instruction after LDL);
-//   320 / 288 threads: ptxas stays at 168 registers and spills all the same: 5.1e8 / 8.1e8, 4.6e8 / 7.3e8;
-//   256 threads, 255 registers, no spills (8 warps per SM): 5.9e8 / 9.0e8  <- this one
-//   224 / 192 threads: 5.0e8 / 7.8e8, 4.3e8 / 6.7e8 (too few warps).
-#ifndef F16_LF_THREADS
-#define F16_LF_THREADS 256
+// CTA size and scheme.  The kernel is instantiated per scheme: with the scheme a compile-time constant the forward kernel has no
+// second pass, no stash and no stash memory (L1 keeps 90 KB instead of 8), the central kernel no base-point shuffles.  Measured at
+// 2^20 points, A,B pairs per second:
+//   one kernel for both schemes (scheme a run-time argument), 256 threads / 255 registers: central 6.07e8, forward 9.1e8
+//       (384 threads / 168 registers: 5.6e8 / 7.9e8 -- two spills, reloaded from L2 with 220 KB of shared memory in use;
+//        320 / 288 / 224 / 192 threads: all slower)
+//   per-scheme kernels, 256 threads both: central 6.27e8, forward 1.08e9
+//   forward kernel at 384 threads / 168 registers (12 warps per SM; its 24 bytes of spills stay in L1): 1.11e9  <- forward
+//   forward kernel at 320 threads: 1.00e9 (uneven warps per scheduler)
+//   central kernel: 256 threads / 255 registers, no spills (the 55 KB stash of a 384-thread CTA leaves no L1)  <- central
+#ifndef F16_LF_THREADS_CENTRAL
+#define F16_LF_THREADS_CENTRAL 256
 #endif
-constexpr int LF_THREADS = F16_LF_THREADS;
+#ifndef F16_LF_THREADS_FORWARD
+#define F16_LF_THREADS_FORWARD 384
+#endif
+constexpr int LF_THREADS_CENTRAL = F16_LF_THREADS_CENTRAL, LF_THREADS_FORWARD = F16_LF_THREADS_FORWARD;
 constexpr int LF_IN_LD = 24;  // 18 states + 4 inputs (+ 2 pad) per staged aircraft
 
-template <int FI>
+template <int FI, int THREADS, bool CENTRAL>
 struct LfSmem {
   static constexpr int IMG_BYTES = FI ? F16_FI_BYTES : F16_LOFI_STEP_IMG_DOUBLES * 8;
   static constexpr int BAR_OFF = (IMG_BYTES + 15) / 16 * 16;
   static constexpr int STASH_OFF = (BAR_OFF + 16 + 127) / 128 * 128;
-  static constexpr int IN_OFF = STASH_OFF + 18 * LF_THREADS * 8;  // stash: f(x + eps e_c) of the central scheme, [18][thread]
-  static constexpr int TOTAL = IN_OFF + (LF_THREADS / 32) * 2 * 2 * LF_IN_LD * 8;  // per warp: 2 stages x 2 aircraft x 24 doubles
+  // stash: f(x + eps e_c) of the central scheme, [18][thread]; the forward instantiation has none
+  static constexpr int IN_OFF = STASH_OFF + (CENTRAL ? 18 * THREADS * 8 : 0);
+  static constexpr int TOTAL = IN_OFF + (THREADS / 32) * 2 * 2 * LF_IN_LD * 8;  // per warp: 2 stages x 2 aircraft x 24 doubles
 };
 
 // (f+ - f-) / den (the reference divides, env.py:330,339).  The reference-order pass forms the IEEE quotient (div_by); the fast
@@ -192,12 +199,15 @@ static __device__ __noinline__ void lin_redo_pass(DevTables tabs, BatchSel sel, 
   }
 }
 
-template <int FI>
+// One instantiation per scheme (the scheme is a compile-time constant inside: the forward kernel carries no second pass, no stash
+// and no stash memory) and CTA size (LF_THREADS_FORWARD / LF_THREADS_CENTRAL above).
+template <int FI, int LF_THREADS, bool CENTRAL>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 linearise_fast_kernel(DevTables tabs, BatchSel sel, const double* __restrict__ x_g, long long ld_x, const double* __restrict__ u_g,
-                      long long ld_u, long long N, double eps, int scheme, double* __restrict__ A_g, double* __restrict__ B_g,
+                      long long ld_u, long long N, double eps, double* __restrict__ A_g, double* __restrict__ B_g,
                       int* __restrict__ status, unsigned* __restrict__ redo) {
-  using S = LfSmem<FI>;
+  using S = LfSmem<FI, LF_THREADS, CENTRAL>;
+  constexpr int scheme = CENTRAL ? 1 : 0;
   const double* img = reinterpret_cast<const double*>(f16_smem);
   if (FI) {
     stage_tables_tma<F16_FI_BYTES>(f16_smem, tabs.hifi_fast, reinterpret_cast<unsigned long long*>(f16_smem + S::BAR_OFF));
@@ -351,12 +361,16 @@ cudaError_t launch_linearise_fast(const LaunchCfg& cfg, const DevTables& tabs, c
   const long long n_tasks = (N + 1) / 2;
   cudaError_t e = cudaSuccess;
   const bool want1 = sel.fi != nullptr || sel.fi_default != 0, want0 = sel.fi != nullptr || sel.fi_default == 0;
+  auto go = [&](auto kern, int threads, int smem) {
+    return launch_persistent(cfg, kern, threads, smem, n_tasks, threads / 32, tabs, sel, x, ld_x, u, ld_u, N, eps, A, B, status, redo);
+  };
+  constexpr int TC = LF_THREADS_CENTRAL, TF = LF_THREADS_FORWARD;
   if (want1)
-    e = launch_persistent(cfg, linearise_fast_kernel<1>, LF_THREADS, LfSmem<1>::TOTAL, n_tasks, LF_THREADS / 32, tabs, sel, x, ld_x, u,
-                          ld_u, N, eps, scheme, A, B, status, redo);
+    e = scheme != 0 ? go(linearise_fast_kernel<1, TC, true>, TC, LfSmem<1, TC, true>::TOTAL)
+                    : go(linearise_fast_kernel<1, TF, false>, TF, LfSmem<1, TF, false>::TOTAL);
   if (e == cudaSuccess && want0)
-    e = launch_persistent(cfg, linearise_fast_kernel<0>, LF_THREADS, LfSmem<0>::TOTAL, n_tasks, LF_THREADS / 32, tabs, sel, x, ld_x, u,
-                          ld_u, N, eps, scheme, A, B, status, redo);
+    e = scheme != 0 ? go(linearise_fast_kernel<0, TC, true>, TC, LfSmem<0, TC, true>::TOTAL)
+                    : go(linearise_fast_kernel<0, TF, false>, TF, LfSmem<0, TF, false>::TOTAL);
   return e;
 }
 

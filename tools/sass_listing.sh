@@ -13,7 +13,8 @@ list() {  # <out-name> <mangled-name substring>
 list step_hifi_fast_chunked step_hifi_fast_chunked_kernelILb0ELi0E
 list step_hifi_fast_plain step_hifi_fast_kernelILb1ELb0ELi384ELi0E
 list step_hifi_fast_lqr_mpc_columns step_hifi_fast_kernelILb1ELb1ELi384ELi14880664E
-list linearise_fast_hifi linearise_fast_kernelILi1E
+list linearise_fast_hifi linearise_fast_kernelILi1ELi256ELb1E
+list linearise_fast_hifi_forward linearise_fast_kernelILi1ELi384ELb0E
 list xdot_fast_hifi_calc_xdot xdot_fast_kernelILi1ELb0ELi256E
 list xdot_fast_hifi_nlplant xdot_fast_kernelILi1ELb1ELi384E
 list stats_partial stats14partial_kernel
